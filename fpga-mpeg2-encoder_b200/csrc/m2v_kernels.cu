@@ -1,0 +1,719 @@
+// m2v_kernels.cu - sm_100a kernels of the MPEG-2 I/P macroblock path.
+//
+//   K1 mb_encode : one warp per macroblock.  4:4:4->4:2:0 chroma subsample, full-search SAD motion
+//                  estimation, half-pel refinement, intra/inter decision, prediction, 6x 8x8 integer
+//                  DCT, quantise, zig-zag, dequantise, Chen-Wang IDCT, reconstruction.
+//   K2 vlc       : one warp per macroblock.  run/level + VLC; warp scan over per-coefficient code
+//                  lengths; count pass and write pass.
+//   K3 scans     : slice -> frame -> batch prefix sums of bit/byte lengths; K4 writes the headers.
+//
+// Behaviour follows /root/reference/RTL/mpeg2encoder.v ("RTL") stage by stage; the citations say
+// which lines each block reproduces.  All arithmetic is integer and must be bit-exact.
+#include "m2v_kernels.cuh"
+#include "m2v_tables.cuh"
+#include <stdio.h>
+
+#define FULL 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------
+// device tables
+// ------------------------------------------------------------------------------------------------
+__constant__ uint32_t c_vlc_motion[17];
+__constant__ uint32_t c_vlc_cbp[64];
+__constant__ uint32_t c_vlc_dcy[12];
+__constant__ uint32_t c_vlc_dcc[12];
+__device__ uint32_t d_vlc_ac[32 * M2V_AC_LEVELS];
+struct QEntry { uint32_t W, recip, off, zz; };          // per coefficient position i*8+j
+__device__ QEntry d_qtab[4][64];                        // [Q_LEVEL-1]
+
+cudaError_t m2v_upload_tables(int) {
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_vlc_motion, M2V_VLC_MOTION, sizeof(M2V_VLC_MOTION)))) return e;
+    if ((e = cudaMemcpyToSymbol(c_vlc_cbp, M2V_VLC_CBP, sizeof(M2V_VLC_CBP)))) return e;
+    if ((e = cudaMemcpyToSymbol(c_vlc_dcy, M2V_VLC_DC_Y, sizeof(M2V_VLC_DC_Y)))) return e;
+    if ((e = cudaMemcpyToSymbol(c_vlc_dcc, M2V_VLC_DC_C, sizeof(M2V_VLC_DC_C)))) return e;
+    if ((e = cudaMemcpyToSymbol(d_vlc_ac, M2V_VLC_AC, sizeof(M2V_VLC_AC)))) return e;
+    static QEntry h[4][64];
+    for (int q = 1; q <= 4; q++)
+        for (int i = 0; i < 64; i++) {
+            uint32_t w = M2V_INTRA_Q[i];
+            h[q - 1][i].W = w;
+            // floor(n / w) == umulhi(n, ceil(2^32 / w)) for every n < 2^15 (checked in tests/test_host_logic.py)
+            h[q - 1][i].recip = (uint32_t)((0x100000000ull + w - 1) / w);
+            h[q - 1][i].off = (w * ((3u << q) + 2u)) >> 3;            // RTL:2072
+            h[q - 1][i].zz = M2V_ZIGZAG[i];
+        }
+    return cudaMemcpyToSymbol(d_qtab, h, sizeof(h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ uint32_t exlo(uint32_t v) { return __byte_perm(v, 0, 0x4140); }   // bytes 0,1 -> halfwords
+__device__ __forceinline__ uint32_t exhi(uint32_t v) { return __byte_perm(v, 0, 0x4342); }   // bytes 2,3 -> halfwords
+__device__ __forceinline__ uint32_t pack4(uint32_t h0, uint32_t h1) { return __byte_perm(h0, h1, 0x6420); }
+// mean4 on packed halfwords: (s + 1) >> 2 with the RTL's +1 rounding (RTL:760-767)
+__device__ __forceinline__ uint32_t m4h(uint32_t s) { return ((s + 0x00010001u) >> 2) & 0x00FF00FFu; }
+
+// RTL:804-840
+__device__ __forceinline__ int find_min10(const int v[10]) {
+    int i01 = v[1] < v[0], m01 = i01 ? v[1] : v[0];
+    int i23 = v[3] < v[2], m23 = i23 ? v[3] : v[2];
+    int i45 = v[5] < v[4], m45 = i45 ? v[5] : v[4];
+    int i67 = v[7] < v[6], m67 = i67 ? v[7] : v[6];
+    int i89 = v[9] < v[8], m89 = i89 ? v[9] : v[8];
+    int h03 = m23 < m01, m03 = h03 ? m23 : m01;
+    int h47 = m67 < m45, m47 = h47 ? m67 : m45;
+    if (m89 <= m03 && m89 <= m47) return 8 + i89;
+    if (m03 < m47) return h03 ? 2 + i23 : i01;
+    return h47 ? 6 + i67 : 4 + i45;
+}
+
+// forward 8-point transform with the RTL's 8-bit matrix (RTL:102-112), exact integer butterflies
+__device__ __forceinline__ void fdct8(const int x[8], int o[8]) {
+    int e0 = x[0] + x[7], e1 = x[1] + x[6], e2 = x[2] + x[5], e3 = x[3] + x[4];
+    int d0 = x[0] - x[7], d1 = x[1] - x[6], d2 = x[2] - x[5], d3 = x[3] - x[4];
+    int ee0 = e0 + e3, ee1 = e1 + e2, eo0 = e0 - e3, eo1 = e1 - e2;
+    o[0] = 64 * (ee0 + ee1);
+    o[4] = 64 * (ee0 - ee1);
+    o[2] = 84 * eo0 + 35 * eo1;
+    o[6] = 35 * eo0 - 84 * eo1;
+    o[1] = 89 * d0 + 75 * d1 + 50 * d2 + 18 * d3;
+    o[3] = 75 * d0 - 18 * d1 - 89 * d2 - 50 * d3;
+    o[5] = 50 * d0 - 89 * d1 + 18 * d2 + 75 * d3;
+    o[7] = 18 * d0 - 50 * d1 + 75 * d2 - 89 * d3;
+}
+
+#define W1 2841u
+#define W2 2676u
+#define W3 2408u
+#define W5 1609u
+#define W6 1108u
+#define W7 565u
+__device__ __forceinline__ int sx18(int v) { return (int)((uint32_t)v << 14) >> 14; }
+
+// Chen-Wang rows (RTL:849-904): 13-bit in, 18-bit out.  The RTL computes in 32-bit registers that
+// wrap; unsigned arithmetic reproduces that without relying on signed overflow.
+typedef uint32_t u32;
+__device__ __forceinline__ int sra(u32 v, int s) { return (int)v >> s; }
+__device__ __forceinline__ void idct_row(const int a[8], int r[8]) {
+    u32 x0 = ((u32)a[0] << 11) + 128u, x1 = (u32)a[4] << 11, x2 = a[6], x3 = a[2], x4 = a[1], x5 = a[7], x6 = a[5], x7 = a[3], x8;
+    x8 = W7 * (x4 + x5); x4 = x8 + (W1 - W7) * x4; x5 = x8 - (W1 + W7) * x5;
+    x8 = W3 * (x6 + x7); x6 = x8 - (W3 - W5) * x6; x7 = x8 - (W3 + W5) * x7;
+    x8 = x0 + x1; x0 = x0 - x1;
+    x1 = W6 * (x3 + x2); x2 = x1 - (W2 + W6) * x2; x3 = x1 + (W2 - W6) * x3;
+    x1 = x4 + x6; x4 = x4 - x6; x6 = x5 + x7; x5 = x5 - x7;
+    x7 = x8 + x3; x8 = x8 - x3; x3 = x0 + x2; x0 = x0 - x2;
+    x2 = (u32)sra(181u * (x4 + x5) + 128u, 8); x4 = (u32)sra(181u * (x4 - x5) + 128u, 8);
+    r[0] = sx18(sra(x7 + x1, 8)); r[1] = sx18(sra(x3 + x2, 8)); r[2] = sx18(sra(x0 + x4, 8)); r[3] = sx18(sra(x8 + x6, 8));
+    r[4] = sx18(sra(x8 - x6, 8)); r[5] = sx18(sra(x0 - x4, 8)); r[6] = sx18(sra(x3 - x2, 8)); r[7] = sx18(sra(x7 - x1, 8));
+}
+__device__ __forceinline__ int clip255(int v) { return v < -255 ? -255 : v > 255 ? 255 : v; }
+// Chen-Wang columns (RTL:916-970): 18-bit in, 9-bit clipped out
+__device__ __forceinline__ void idct_col(const int a[8], int o[8]) {
+    u32 x0 = ((u32)a[0] << 8) + 8192u, x1 = (u32)a[4] << 8, x2 = a[6], x3 = a[2], x4 = a[1], x5 = a[7], x6 = a[5], x7 = a[3], x8;
+    x8 = W7 * (x4 + x5) + 4u; x4 = (u32)sra(x8 + (W1 - W7) * x4, 3); x5 = (u32)sra(x8 - (W1 + W7) * x5, 3);
+    x8 = W3 * (x6 + x7) + 4u; x6 = (u32)sra(x8 - (W3 - W5) * x6, 3); x7 = (u32)sra(x8 - (W3 + W5) * x7, 3);
+    x8 = x0 + x1; x0 = x0 - x1;
+    x1 = W6 * (x3 + x2) + 4u; x2 = (u32)sra(x1 - (W2 + W6) * x2, 3); x3 = (u32)sra(x1 + (W2 - W6) * x3, 3);
+    x1 = x4 + x6; x4 = x4 - x6; x6 = x5 + x7; x5 = x5 - x7;
+    x7 = x8 + x3; x8 = x8 - x3; x3 = x0 + x2; x0 = x0 - x2;
+    x2 = (u32)sra(181u * (x4 + x5) + 128u, 8); x4 = (u32)sra(181u * (x4 - x5) + 128u, 8);
+    o[0] = clip255(sra(x7 + x1, 14)); o[1] = clip255(sra(x3 + x2, 14)); o[2] = clip255(sra(x0 + x4, 14)); o[3] = clip255(sra(x8 + x6, 14));
+    o[4] = clip255(sra(x8 - x6, 14)); o[5] = clip255(sra(x0 - x4, 14)); o[6] = clip255(sra(x3 - x2, 14)); o[7] = clip255(sra(x7 - x1, 14));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+#define K1_WARPS 8
+#define TSTR 72                      // padded tile stride (words) of the transform scratch
+struct __align__(16) WarpSmem {
+    uint32_t curY[16][4];            // current luma block, 16 rows x 16 B
+    uint32_t curC[2][8][2];          // current 4:2:0 chroma blocks
+    uint32_t winY[30][8];            // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-8..X0+23
+    uint32_t winC[2][16][4];         // chroma windows: rows 8by-4..8by+11, bytes 8bx-4..8bx+11
+    int16_t res[6][64];              // residual, later the zig-zag levels
+    uint8_t pred[6][64];             // prediction, later the reconstruction
+    int32_t tmp[6 * TSTR];           // transform scratch
+};
+
+struct K1Args {
+    const uint8_t *in; uint8_t *rec; const uint8_t *ref;   // rec/ref: [G][W*H*3/2]
+    int16_t *coefs; uint32_t *mbinfo;
+    int W, H, mbw, mbh, nmb, P, Q, t;
+    long total;                                             // ngops_t * nmb
+};
+
+template <int VL, bool PFRAME>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
+    constexpr int R = 2 * VL;
+    constexpr int WROWS = 18 + 2 * R;
+    __shared__ WarpSmem smem[K1_WARPS];
+    __shared__ QEntry qt[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) qt[threadIdx.x] = d_qtab[p.Q - 1][threadIdx.x];
+    __syncthreads();
+    const long gw = (long)blockIdx.x * K1_WARPS + warp;
+    if (gw >= p.total) return;
+    WarpSmem &s = smem[warp];
+    const int g = (int)(gw / p.nmb), mb = (int)(gw % p.nmb), by = mb / p.mbw, bx = mb % p.mbw;
+    const long n = (long)g * (p.P + 1) + p.t;               // frame index inside the batch
+    const int W = p.W, H = p.H, CW = W >> 1;
+    const int Y0 = by * 16, X0 = bx * 16;
+    const size_t ysz = (size_t)W * H;
+    const uint8_t *fin = p.in + (size_t)n * 3 * ysz;
+
+    // ---- current block: Y as is; U,V 4:4:4 -> 4:2:0 = mean2 of pixel pairs, then mean2 of the two
+    //      horizontally subsampled rows (RTL:1086-1089, 1167-1170) -------------------------------
+    if (lane < 16) {
+        uint4 v = __ldg((const uint4 *)(fin + (size_t)(Y0 + lane) * W + X0));
+        *(uint4 *)s.curY[lane] = v;
+    }
+    {
+        const int comp = lane >> 4, r = lane & 15;
+        uint4 v = __ldg((const uint4 *)(fin + (1 + comp) * ysz + (size_t)(Y0 + r) * W + X0));
+        uint32_t h0 = __vavgu4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
+        uint32_t h1 = __vavgu4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
+        uint32_t g0 = __shfl_xor_sync(FULL, h0, 1), g1 = __shfl_xor_sync(FULL, h1, 1);
+        if (!(r & 1)) { s.curC[comp][r >> 1][0] = __vavgu4(g0, h0); s.curC[comp][r >> 1][1] = __vavgu4(g1, h1); }
+    }
+
+    int inter = 0, mvx = 0, mvy = 0;
+    if (PFRAME) {
+        // ---- reference windows (RTL:1350-1425, 1613-1629).  Out-of-frame bytes are zero; they only
+        //      ever feed candidates the border rule disables (RTL:1642-1645, 1757-1760). -----------
+        const uint8_t *rY = p.ref + (size_t)g * (ysz * 3 / 2);
+        for (int i = lane; i < WROWS * 4; i += 32) {
+            int r = i >> 2, seg = i & 3, yy = Y0 - (R + 1) + r, xx = X0 - 8 + seg * 8;
+            uint2 v = make_uint2(0, 0);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *(const uint2 *)(rY + (size_t)yy * W + xx);
+            *(uint2 *)&s.winY[r][seg * 2] = v;
+        }
+        for (int i = lane; i < 128; i += 32) {
+            int comp = i >> 6, r = (i >> 2) & 15, seg = i & 3, yy = by * 8 - 4 + r, xx = bx * 8 - 4 + seg * 4;
+            uint32_t v = 0;
+            if (yy >= 0 && yy < (H >> 1) && xx >= 0 && xx < CW)
+                v = *(const uint32_t *)(rY + ysz + comp * (ysz >> 2) + (size_t)yy * CW + xx);
+            s.winC[comp][r][seg] = v;
+        }
+    }
+    __syncwarp();
+
+    if (PFRAME) {
+        // ---- full-pel search (RTL:1634-1715).  lane = dxi + 16*half: candidate column dx = dxi-R,
+        //      half = which 8 bytes of every 16-byte row.  Each lane keeps 2R+1 accumulators (one
+        //      per dy) and walks the window rows once.
+        int fmvy = 0, fmvx = 0;
+        {
+            const int half = lane >> 4;
+            int dxi = lane & 15; if (dxi > 2 * R) dxi = 2 * R;
+            uint32_t cur[16][2];
+#pragma unroll
+            for (int y = 0; y < 16; y++) { cur[y][0] = s.curY[y][half * 2]; cur[y][1] = s.curY[y][half * 2 + 1]; }
+            uint32_t acc[2 * R + 1];
+#pragma unroll
+            for (int i = 0; i <= 2 * R; i++) acc[i] = 0;
+            const int o = 8 + (dxi - R) + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
+#pragma unroll
+            for (int wr = 0; wr < 16 + 2 * R; wr++) {       // reference row Y0 - R + wr  = window row wr+1
+                uint32_t w0 = s.winY[wr + 1][wi], w1 = s.winY[wr + 1][wi + 1], w2 = s.winY[wr + 1][wi + 2];
+                uint32_t a = fsr(w0, w1, sh), b = fsr(w1, w2, sh);
+#pragma unroll
+                for (int dyi = 0; dyi <= 2 * R; dyi++) {
+                    const int cy = wr - dyi;
+                    if (cy >= 0 && cy < 16) {
+                        acc[dyi] = __vsadu4(a, cur[cy][0]) + acc[dyi];
+                        acc[dyi] = __vsadu4(b, cur[cy][1]) + acc[dyi];
+                    }
+                }
+            }
+            uint32_t best = 0xFFFFFFFFu;
+            const int dx = (lane & 15) - R;
+#pragma unroll
+            for (int dyi = 0; dyi <= 2 * R; dyi++) {
+                uint32_t tot = acc[dyi] + __shfl_xor_sync(FULL, acc[dyi], 16);
+                const int dy = dyi - R;
+                bool dis = (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0) || (by == 0 && dy < 0) || (by == p.mbh - 1 && dy > 0);
+                // SAD >= 4096 disqualifies (RTL:1669-1670); ties: largest dy, then largest dx (RTL:1696-1710)
+                if (lane <= 2 * R && !dis && tot < 4096u) best = min(best, (tot << 10) | ((uint32_t)(R - dy) << 5) | (uint32_t)(R - dx));
+            }
+            best = __reduce_min_sync(FULL, best);
+            if (best != 0xFFFFFFFFu) { fmvy = R - (int)((best >> 5) & 31); fmvx = R - (int)(best & 31); }
+        }
+
+        // ---- half-pel refinement + intra/inter decision (RTL:1743-1816).  lane = 2*y + half. ----
+        const int y = lane >> 1, half = lane & 1;
+        const uint32_t c0 = s.curY[y][half * 2], c1 = s.curY[y][half * 2 + 1];
+        uint32_t cand[9][2];
+        {
+            const int wr0 = (R + 1) + fmvy + y - 1;
+            const int o = 7 + fmvx + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
+            uint32_t zm[3][2], zz[3][2], zp[3][2];           // bytes x-1, x, x+1 of rows y-1,y,y+1
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                const uint32_t *row = s.winY[wr0 + rr];
+                uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2], w3 = row[min(wi + 3, 7)];
+                uint32_t v0 = fsr(w0, w1, sh), v1 = fsr(w1, w2, sh), v2 = fsr(w2, w3, sh);
+                zm[rr][0] = v0; zm[rr][1] = v1;
+                zz[rr][0] = fsr(v0, v1, 8); zz[rr][1] = fsr(v1, v2, 8);
+                zp[rr][0] = fsr(v0, v1, 16); zp[rr][1] = fsr(v1, v2, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                cand[4][k] = zz[1][k];                                            // f_Y_hlf even,even
+                cand[3][k] = __vavgu4(zm[1][k], zz[1][k]);                        // mean2 left   (RTL:1749)
+                cand[5][k] = __vavgu4(zz[1][k], zp[1][k]);                        // mean2 right
+                cand[1][k] = __vavgu4(zz[0][k], zz[1][k]);                        // mean2 up     (RTL:1750)
+                cand[7][k] = __vavgu4(zz[1][k], zz[2][k]);                        // mean2 down
+                // diagonals: mean4 with +1 rounding (RTL:1751, 764) on packed halfwords
+                uint32_t pm[3][2], pp[3][2];                                      // pair sums (x-1,x) and (x,x+1), per row
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) {
+                    uint32_t zl = exlo(zz[rr][k]), zh = exhi(zz[rr][k]);
+                    pm[rr][0] = exlo(zm[rr][k]) + zl; pm[rr][1] = exhi(zm[rr][k]) + zh;
+                    pp[rr][0] = exlo(zp[rr][k]) + zl; pp[rr][1] = exhi(zp[rr][k]) + zh;
+                }
+                cand[0][k] = pack4(m4h(pm[0][0] + pm[1][0]), m4h(pm[0][1] + pm[1][1]));
+                cand[2][k] = pack4(m4h(pp[0][0] + pp[1][0]), m4h(pp[0][1] + pp[1][1]));
+                cand[6][k] = pack4(m4h(pm[1][0] + pm[2][0]), m4h(pm[1][1] + pm[2][1]));
+                cand[8][k] = pack4(m4h(pp[1][0] + pp[2][0]), m4h(pp[1][1] + pp[2][1]));
+            }
+        }
+        int key[10];
+        {
+            const bool xn = (bx == 0 || fmvx == -R), xp = (bx == p.mbw - 1 || fmvx == R);
+            const bool yn = (by == 0 || fmvy == -R), yp = (by == p.mbh - 1 || fmvy == R);
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                uint32_t sd = __vsadu4(cand[i][0], c0) + __vsadu4(cand[i][1], c1);
+                sd = __reduce_add_sync(FULL, sd);
+                const int cy = i / 3 - 1, cx = i % 3 - 1;
+                bool dis = (cx < 0 && xn) || (cx > 0 && xp) || (cy < 0 && yn) || (cy > 0 && yp);   // RTL:1757-1760
+                key[i] = (dis || sd >= 4096u) ? 8191 : (int)sd;
+            }
+            // intra key: pixel sum + sum|pixel-mean|, 16 bit, saturated to 4095 (RTL:1600,1662,1744,1776-1777,1791)
+            uint32_t S = __reduce_add_sync(FULL, __vsadu4(c0, 0) + __vsadu4(c1, 0));
+            uint32_t m = (S >> 8) & 0xFF; m |= m << 8; m |= m << 16;
+            uint32_t D = __reduce_add_sync(FULL, __vsadu4(c0, m) + __vsadu4(c1, m));
+            uint32_t T = (S + D) & 0xFFFF;
+            key[9] = T < 4096u ? (int)T : 4095;
+        }
+        const int w = find_min10(key);
+        inter = (w != 9);
+        const int hy = inter ? w / 3 - 1 : 0, hx = inter ? w % 3 - 1 : 0;
+        mvy = 2 * fmvy + hy; mvx = 2 * fmvx + hx;              // RTL:1827-1828
+
+        // ---- luma prediction + residual (RTL:1891-1897, 1980-2002) -----------------------------
+        uint32_t p0 = 0x80808080u, p1 = 0x80808080u;
+        if (inter) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) if (w == i) { p0 = cand[i][0]; p1 = cand[i][1]; }
+        }
+        {
+            const int tile = (y >> 3) * 2 + half, r = y & 7;
+            *(uint2 *)&s.pred[tile][r * 8] = make_uint2(p0, p1);
+            uint4 rv;
+            rv.x = __vsub2(exlo(c0), exlo(p0)); rv.y = __vsub2(exhi(c0), exhi(p0));
+            rv.z = __vsub2(exlo(c1), exlo(p1)); rv.w = __vsub2(exhi(c1), exhi(p1));
+            *(uint4 *)&s.res[tile][r * 8] = rv;
+        }
+        // ---- chroma prediction + residual (RTL:1847-1888, 1899-1916).  lane = comp*16 + y*2 + half.
+        {
+            const int comp = lane >> 4, cyy = (lane >> 1) & 7, ch = lane & 1;
+            const uint32_t cc = s.curC[comp][cyy][ch];
+            uint32_t pc = 0x80808080u;
+            if (inter) {
+                const int cyv = mvy >> 1, cxv = mvx >> 1;          // floor (RTL:1904-1910)
+                const int fy = cyv >> 1, fx = cxv >> 1, oy = cyv & 1, ox = cxv & 1;
+                const int row = 4 + cyy + fy, o = 4 + 4 * ch + fx, wi = o >> 2, sh = (o & 3) * 8;
+                unsigned long long t0 = ((unsigned long long)s.winC[comp][row][wi + 1] << 32 | s.winC[comp][row][wi]) >> sh;
+                unsigned long long t1 = ((unsigned long long)s.winC[comp][row + 1][wi + 1] << 32 | s.winC[comp][row + 1][wi]) >> sh;
+                uint32_t a0 = (uint32_t)t0, a1 = (uint32_t)(t0 >> 8), b0 = (uint32_t)t1, b1 = (uint32_t)(t1 >> 8);
+                if (oy && ox) {
+                    uint32_t lo = exlo(a0) + exlo(a1) + exlo(b0) + exlo(b1), hi = exhi(a0) + exhi(a1) + exhi(b0) + exhi(b1);
+                    pc = pack4(m4h(lo), m4h(hi));
+                } else if (ox) pc = __vavgu4(a0, a1);
+                else if (oy) pc = __vavgu4(a0, b0);
+                else pc = a0;
+            }
+            *(uint32_t *)&s.pred[4 + comp][cyy * 8 + ch * 4] = pc;
+            uint2 rv; rv.x = __vsub2(exlo(cc), exlo(pc)); rv.y = __vsub2(exhi(cc), exhi(pc));
+            *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = rv;
+        }
+    } else {
+        // I-frame: every macroblock intra, predictor 128, vector 0 (RTL:1820-1825, 1894-1903)
+        const int y = lane >> 1, half = lane & 1;
+        const uint32_t c0 = s.curY[y][half * 2], c1 = s.curY[y][half * 2 + 1], pz = 0x80808080u;
+        const int tile = (y >> 3) * 2 + half, r = y & 7;
+        *(uint2 *)&s.pred[tile][r * 8] = make_uint2(pz, pz);
+        uint4 rv;
+        rv.x = __vsub2(exlo(c0), exlo(pz)); rv.y = __vsub2(exhi(c0), exhi(pz));
+        rv.z = __vsub2(exlo(c1), exlo(pz)); rv.w = __vsub2(exhi(c1), exhi(pz));
+        *(uint4 *)&s.res[tile][r * 8] = rv;
+        const int comp = lane >> 4, cyy = (lane >> 1) & 7, ch = lane & 1;
+        const uint32_t cc = s.curC[comp][cyy][ch];
+        *(uint32_t *)&s.pred[4 + comp][cyy * 8 + ch * 4] = pz;
+        uint2 rc; rc.x = __vsub2(exlo(cc), exlo(pz)); rc.y = __vsub2(exhi(cc), exhi(pz));
+        *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = rc;
+    }
+    __syncwarp();
+
+    // ---- transform / quantise / scan / reconstruct.  Round 0: luma tiles on 32 lanes (tile = lane>>3,
+    //      vector = lane&7); round 1: chroma tiles on 16 lanes.  (RTL:2029-2077, 2128-2356, 2452-2467)
+    int cbp = 0;
+    const int Q = p.Q;
+#pragma unroll 1
+    for (int round = 0; round < 2; round++) {
+        const bool act = (round == 0) || lane < 16;
+        const int tile = round * 4 + (lane >> 3), v = lane & 7;
+        int32_t *tt = s.tmp + tile * TSTR;
+        int x[8], o[8];
+        if (act) {                                               // rows: A = R * DCTM^T (RTL:2029-2036)
+            uint4 rv = *(const uint4 *)&s.res[tile][v * 8];
+            x[0] = (int16_t)(rv.x & 0xFFFF); x[1] = (int32_t)rv.x >> 16; x[2] = (int16_t)(rv.y & 0xFFFF); x[3] = (int32_t)rv.y >> 16;
+            x[4] = (int16_t)(rv.z & 0xFFFF); x[5] = (int32_t)rv.z >> 16; x[6] = (int16_t)(rv.w & 0xFFFF); x[7] = (int32_t)rv.w >> 16;
+            fdct8(x, o);
+#pragma unroll
+            for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
+        }
+        __syncwarp();
+        bool nzl = false;
+        if (act) {                                               // columns: B = DCTM * A, round, quantise
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
+            fdct8(x, o);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const QEntry qe = qt[i * 8 + v];
+                const int C = (o[i] + 2048) >> 12;                                   // RTL:2058
+                const uint32_t a = (uint32_t)abs(C);
+                uint32_t yq;
+                if (inter) yq = (a + 2) >> (4 + Q);                                  // RTL:2070
+                else if (i | v) yq = __umulhi((a + qe.off) >> Q, qe.recip);          // RTL:2072 (exact division)
+                else yq = (a >> 4) + ((a >> 3) & 1);                                 // RTL:2074
+                yq = min(yq, 2047u);                                                 // RTL:2075
+                const int q = C < 0 ? -(int)yq : (int)yq;
+                s.res[tile][qe.zz] = (int16_t)q;                                     // zig-zag (RTL:2464)
+                nzl |= (q != 0);
+                int xq;                                                              // dequantise (RTL:2132-2147)
+                if (inter) { xq = 2 * q + (q > 0) - (q < 0); xq <<= Q; xq = max(-2047, min(2047, xq)); }
+                else if (i | v) { xq = q * (int)qe.W; xq = (Q >= 3) ? (xq << (Q - 3)) : (xq >> (3 - Q)); xq = max(-2047, min(2047, xq)); }
+                else xq = 2 * q;
+                o[i] = xq;
+            }
+        }
+        __syncwarp();                                            // all column reads of A done before overwrite
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) tt[i * 8 + v] = o[i];
+        }
+        const uint32_t nzm = __ballot_sync(FULL, act && nzl);
+        if (round == 0) { for (int k = 0; k < 4; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (32 >> k) : 0; }
+        else { for (int k = 0; k < 2; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (2 >> k) : 0; }
+        __syncwarp();
+        if (act) {                                               // inverse rows (in place)
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = tt[v * 8 + j];
+            idct_row(x, o);
+#pragma unroll
+            for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
+        }
+        __syncwarp();
+        if (act) {                                               // inverse columns, add prediction, clip (RTL:2352)
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
+            idct_col(x, o);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int r = (int)s.pred[tile][i * 8 + v] + o[i];
+                s.pred[tile][i * 8 + v] = (uint8_t)max(0, min(255, r));
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- outputs: reconstruction (next frame's reference), levels, record -----------------------
+    {
+        uint8_t *oY = p.rec + (size_t)g * (ysz * 3 / 2);
+        const int y = lane >> 1, half = lane & 1, tile = (y >> 3) * 2 + half;
+        *(uint2 *)(oY + (size_t)(Y0 + y) * W + X0 + 8 * half) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
+        if (lane < 16) {
+            const int comp = lane >> 3, cyy = lane & 7;
+            *(uint2 *)(oY + ysz + comp * (ysz >> 2) + (size_t)(by * 8 + cyy) * CW + bx * 8) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
+        }
+        const size_t mbi = (size_t)n * p.nmb + mb;
+        uint2 *dst = (uint2 *)(p.coefs + mbi * 384);
+        const uint2 *src = (const uint2 *)&s.res[0][0];
+#pragma unroll
+        for (int k = 0; k < 3; k++) dst[lane + 32 * k] = src[lane + 32 * k];
+        if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
+    }
+}
+
+void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
+    K1Args a;
+    a.in = b.in; a.rec = b.recon[t & 1]; a.ref = b.recon[(t & 1) ^ 1];
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo;
+    a.W = b.g.W; a.H = b.g.H; a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.Q = b.g.Q; a.t = t;
+    a.total = ngops_t * b.g.nmb;
+    const unsigned grid = (unsigned)((a.total + K1_WARPS - 1) / K1_WARPS);
+    if (t == 0) { k1_mb_encode<1, false><<<grid, K1_WARPS * 32, 0, st>>>(a); return; }
+    switch (b.g.VL) {
+        case 1: k1_mb_encode<1, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
+        case 2: k1_mb_encode<2, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
+        default: k1_mb_encode<3, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: entropy layer of one macroblock per warp (RTL:2718-2847)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_bits(uint32_t *words, unsigned long long pos, uint32_t code, int len) {
+    if (len <= 0) return;
+    const unsigned long long w = pos >> 5;
+    const int o = (int)(pos & 31);
+    const unsigned long long v = (unsigned long long)code << (64 - len - o);
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    atomicOr(&words[w], __byte_perm(hi, 0, 0x0123));
+    if (lo) atomicOr(&words[w + 1], __byte_perm(lo, 0, 0x0123));
+}
+
+// code for (level v != 0, run) - RTL:2525-2547.  Returns (len<<24 | code) with the sign included.
+__device__ __forceinline__ void ac_code(int v, int run, uint32_t &code, int &len) {
+    const int m = abs(v) - 1;
+    const bool tab = (run == 0 && m < 40) || (run == 1 && m < 18) || (run == 2 && m < 5) || (run == 3 && m < 4) ||
+                     (run >= 4 && ((run <= 6 && m < 3) || (run <= 16 && m < 2) || (run <= 31 && m < 1)));
+    if (tab) {
+        const uint32_t e = __ldg(&d_vlc_ac[run * M2V_AC_LEVELS + m]);
+        code = ((e & 0xFFFF) << 1) | (v < 0);
+        len = (int)(e >> 16) + 1;
+    } else {
+        code = (1u << 18) | ((uint32_t)(run & 63) << 12) | ((uint32_t)v & 0xFFF);
+        len = 24;
+    }
+}
+
+struct K2Args {
+    const int16_t *coefs; const uint32_t *mbinfo;
+    uint32_t *mb_bits; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
+    uint32_t *out;
+    int mbw, mbh, nmb, P; long n0; long total;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k2_vlc(K2Args p) {
+    const int lane = threadIdx.x & 31;
+    const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gw >= p.total) return;
+    const long f = gw / p.nmb;
+    const int mb = (int)(gw % p.nmb), by = mb / p.mbw, bx = mb % p.mbw;
+    const int k = (int)((p.n0 + f) % (p.P + 1));
+    const uint32_t info = p.mbinfo[gw];
+    const int inter = info & 1, mvx = (int8_t)(info >> 8), mvy = (int8_t)(info >> 16), cbp = (info >> 24) & 63;
+    const int16_t *zz = p.coefs + (size_t)gw * 384;
+    // predictors from the left neighbour; reset at slice start (RTL:2713-2715), DC reset by an inter
+    // macroblock (RTL:2786-2792), PMV reset by an intra macroblock (RTL:2771-2773)
+    int pmvx = 0, pmvy = 0, dcp[3] = {0, 0, 0};
+    if (bx > 0) {
+        const uint32_t li = p.mbinfo[gw - 1];
+        if (li & 1) { pmvx = (int8_t)(li >> 8); pmvy = (int8_t)(li >> 16); }
+        else { dcp[0] = zz[-384 + 3 * 64]; dcp[1] = zz[-384 + 4 * 64]; dcp[2] = zz[-384 + 5 * 64]; }
+    }
+    unsigned long long pos = 0;
+    if (WRITE) {
+        const int hdr = (k == 0) ? 25 : 18;
+        pos = 8ull * (p.frame_off[f] + hdr + p.slice_off[f * p.mbh + by]) + p.mb_off[gw];
+    }
+    uint32_t bits = 0;
+    // ---- macroblock header (RTL:2722-2767) ----
+    {
+        uint32_t c; int l;
+        if (!inter && k != 0) { c = 0x23; l = 6; } else if (inter && cbp == 0) { c = 0x09; l = 4; } else { c = 0x03; l = 2; }
+        if (WRITE && lane == 0) put_bits(p.out, pos, c, l);
+        bits += l;
+        if (inter) {
+#pragma unroll
+            for (int comp = 0; comp < 2; comp++) {
+                int d = comp ? mvy - pmvy : mvx - pmvx;
+                if (d > 15) d -= 32; else if (d < -16) d += 32;
+                const uint32_t e = c_vlc_motion[abs(d)];
+                c = e & 0xFFFF; l = (int)(e >> 16);
+                if (d != 0) { c = (c << 1) | (d < 0); l++; }
+                if (WRITE && lane == 0) put_bits(p.out, pos + bits, c, l);
+                bits += l;
+            }
+            const uint32_t e = c_vlc_cbp[cbp];
+            if (WRITE && lane == 0) put_bits(p.out, pos + bits, e & 0xFFFF, (int)(e >> 16));
+            bits += e >> 16;
+        }
+    }
+    // ---- tiles (RTL:2777-2847).  lane L owns scan positions L and L+32. ----
+    int prev_dc = 0;
+#pragma unroll 1
+    for (int t = 0; t < 6; t++) {
+        const int v0 = zz[t * 64 + lane], v1 = zz[t * 64 + 32 + lane];
+        const int dc = __shfl_sync(FULL, v0, 0);
+        const int comp = t < 4 ? 0 : t - 3;
+        const int pred = (t >= 1 && t <= 3) ? prev_dc : dcp[comp];
+        prev_dc = dc;
+        if (!((cbp >> (5 - t)) & 1)) continue;                     // inter tile with no level: nothing (RTL:2799,2804,2828)
+        unsigned long long m = (unsigned long long)__ballot_sync(FULL, v0 != 0) | ((unsigned long long)__ballot_sync(FULL, v1 != 0) << 32);
+        if (!inter) m |= 1ull;                                     // the DC slot always "precedes" the first AC run
+        uint32_t cA = 0, cB = 0; int lA = 0, lB = 0;
+        if (lane == 0) {
+            if (inter) {                                           // RTL:2795-2806
+                if (v0 == 1 || v0 == -1) { cA = 2u | (v0 < 0); lA = 2; }
+                else if (v0 != 0) ac_code(v0, 0, cA, lA);
+            } else {                                               // RTL:2808-2821
+                const int diff = dc - pred, a = abs(diff);
+                const int size = 32 - __clz(a);
+                const uint32_t e = t < 4 ? c_vlc_dcy[size] : c_vlc_dcc[size];
+                const uint32_t db = (uint32_t)(diff < 0 ? diff + (1 << size) - 1 : diff) & ((1u << size) - 1);
+                cA = ((e & 0xFFFF) << size) | db; lA = (int)(e >> 16) + size;
+            }
+        } else if (v0 != 0) {
+            const unsigned long long below = m & ((1ull << lane) - 1);
+            const int prev = below ? 63 - __clzll(below) : -1;
+            ac_code(v0, lane - prev - 1, cA, lA);
+        }
+        if (v1 != 0) {
+            const unsigned long long below = m & ((1ull << (lane + 32)) - 1);
+            const int prev = below ? 63 - __clzll(below) : -1;
+            ac_code(v1, lane + 32 - prev - 1, cB, lB);
+        }
+        // inclusive warp scan of both length streams at once (packed 16+16)
+        uint32_t sc = (uint32_t)lA | ((uint32_t)lB << 16);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += nb; }
+        const uint32_t tot = __shfl_sync(FULL, sc, 31);
+        const uint32_t totA = tot & 0xFFFF, totB = tot >> 16;
+        if (WRITE) {
+            const unsigned long long base = pos + bits;
+            put_bits(p.out, base + ((sc & 0xFFFF) - lA), cA, lA);
+            put_bits(p.out, base + totA + ((sc >> 16) - lB), cB, lB);
+            if (lane == 0) put_bits(p.out, base + totA + totB, 2, 2);      // end of block (RTL:2835,2897-2900)
+        }
+        bits += totA + totB + 2;
+    }
+    if (!WRITE && lane == 0) p.mb_bits[gw] = bits;
+}
+
+void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
+    K2Args a;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
+    a.frame_off = b.frame_off; a.out = b.out_words;
+    a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
+    const unsigned grid = (unsigned)((a.total + 7) / 8);
+    if (write) k2_vlc<true><<<grid, 256, 0, st>>>(a); else k2_vlc<false><<<grid, 256, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: scans.  k3_frame: one CTA per frame - per-slice inclusive scans of macroblock bit lengths,
+// slice byte lengths (38-bit header + macroblocks, zero padded to a byte: RTL:2704-2710, 2940-2943),
+// then the scan over the frame's slices.  k3_batch: one CTA - scan over the frames.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_frame(const uint32_t *mb_bits, uint32_t *mb_off, uint32_t *slice_off,
+                                                uint32_t *frame_bytes, int mbw, int mbh) {
+    __shared__ uint32_t sbytes[128];
+    const long f = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sl = warp; sl < mbh; sl += 8) {
+        const size_t base = ((size_t)f * mbh + sl) * mbw;
+        uint32_t run = 38;                                          // slice header bits
+        for (int c0 = 0; c0 < mbw; c0 += 32) {
+            const int i = c0 + lane;
+            const uint32_t v = i < mbw ? mb_bits[base + i] : 0;
+            uint32_t sc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += nb; }
+            if (i < mbw) mb_off[base + i] = run + sc - v;
+            run += __shfl_sync(FULL, sc, 31);
+        }
+        if (lane == 0) sbytes[sl] = (run + 7) >> 3;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t run = 0;
+        for (int c0 = 0; c0 < mbh; c0 += 32) {
+            const int i = c0 + lane;
+            const uint32_t v = i < mbh ? sbytes[i] : 0;
+            uint32_t sc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += nb; }
+            if (i < mbh) slice_off[f * mbh + i] = run + sc - v;
+            run += __shfl_sync(FULL, sc, 31);
+        }
+        if (lane == 0) frame_bytes[f] = run;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k3_batch(const uint32_t *frame_bytes, unsigned long long *frame_off, long F, long n0, int P) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long c0 = 0; c0 < F; c0 += 1024) {
+        const long i = c0 + threadIdx.x;
+        unsigned long long v = 0;
+        if (i < F) v = (unsigned long long)frame_bytes[i] + (((n0 + i) % (P + 1)) == 0 ? 25 : 18);   // GOP 8 B + picture 17 B | picture 18 B
+        unsigned long long sc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long nb = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += nb; }
+        if (lane == 31) wsum[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane], ws = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned long long nb = __shfl_up_sync(FULL, ws, d); if (lane >= d) ws += nb; }
+            wsum[lane] = ws - w;
+        }
+        __syncthreads();
+        const unsigned long long base = carry + wsum[warp];
+        if (i < F) frame_off[i] = base + sc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + sc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) frame_off[F] = carry;
+}
+
+void m2v_launch_k3_scan(const M2VBatch &b, cudaStream_t st) {
+    k3_frame<<<(unsigned)b.F, 256, 0, st>>>(b.mb_bits, b.mb_off, b.slice_off, b.frame_bytes, b.g.mbw, b.g.mbh);
+    k3_batch<<<1, 1024, 0, st>>>(b.frame_bytes, b.frame_off, b.F, b.n0, b.g.P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: GOP / picture / slice headers (RTL:2645-2656, 2666-2682, 2704-2710).  One thread per slice.
+// ------------------------------------------------------------------------------------------------
+__global__ void k4_headers(uint32_t *out, const unsigned long long *frame_off, const uint32_t *slice_off,
+                           long F, long n0, int P, int mbh, int Q) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * mbh) return;
+    const long f = i / mbh; const int sl = (int)(i % mbh);
+    const long n = n0 + f; const int k = (int)(n % (P + 1));
+    unsigned long long pos = 8ull * frame_off[f];
+    if (sl == 0) {
+        if (k == 0) {                                               // GOP header, time code = absolute frame index
+            long hh = n / 86400; if (hh > 63) hh = 63;
+            put_bits(out, pos, 0x000001, 24); put_bits(out, pos + 24, 0xB8, 8);
+            put_bits(out, pos + 32, (uint32_t)hh, 6); put_bits(out, pos + 38, (uint32_t)((n / 1440) % 60), 6);
+            put_bits(out, pos + 44, 0x40u | (uint32_t)((n / 24) % 60), 7); put_bits(out, pos + 51, (uint32_t)(n % 24), 6);
+            put_bits(out, pos + 57, 2, 2);
+            pos += 64;
+        }
+        put_bits(out, pos, 0x000001, 24); put_bits(out, pos + 24, (uint32_t)k, 18);
+        if (k == 0) { put_bits(out, pos + 42, 0x10000, 19); pos += 64; }
+        else { put_bits(out, pos + 42, 0x20000, 19); put_bits(out, pos + 61, 0x380, 11); pos += 72; }
+        put_bits(out, pos, 0x000001, 24); put_bits(out, pos + 24, 0xB58111, 24); put_bits(out, pos + 48, 0x1BC000, 24);
+    }
+    pos = 8ull * (frame_off[f] + (k == 0 ? 25 : 18) + slice_off[i]);
+    put_bits(out, pos, 0x000001, 24); put_bits(out, pos + 24, (uint32_t)(sl + 1), 8); put_bits(out, pos + 32, (uint32_t)(2 << Q), 6);
+}
+
+void m2v_launch_headers(const M2VBatch &b, cudaStream_t st) {
+    const long n = b.F * b.g.mbh;
+    k4_headers<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.out_words, b.frame_off, b.slice_off, b.F, b.n0, b.g.P, b.g.mbh, b.g.Q);
+}

@@ -1,0 +1,42 @@
+// m2v_kernels.cuh - launch interface between the host state machine (m2v_host.cu) and the
+// sm_100a kernels (m2v_kernels.cu).  Product code; nothing here touches oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// per-macroblock record written by K1, read by K2/K3:
+//   bit 0 inter | bits 8..15 mvx (s8, half-pel) | bits 16..23 mvy | bits 24..29 cbp (Y00 = bit 29)
+#define M2V_INFO(inter, mvx, mvy, cbp) \
+    ((uint32_t)((inter) & 1) | ((uint32_t)((mvx) & 0xFF) << 8) | ((uint32_t)((mvy) & 0xFF) << 16) | ((uint32_t)((cbp) & 63) << 24))
+
+struct M2VGeom {
+    int mbw, mbh, W, H, nmb;   // macroblocks / pixels per frame
+    int P;                     // pframes_count; GOP = P+1 frames
+    int VL, Q;                 // VECTOR_LEVEL, Q_LEVEL
+};
+
+struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
+    M2VGeom g;
+    long F;                    // frames in the batch
+    long n0;                   // absolute index of the first frame (GOP aligned)
+    const uint8_t *in;         // [F][3][H][W] planar yuv444p (device)
+    uint8_t *recon[2];         // ping-pong reconstruction, each [G][W*H*3/2] (device)
+    int16_t *coefs;            // [F][nmb][6][64] quantised levels, zig-zag order
+    uint32_t *mbinfo;          // [F][nmb]
+    uint32_t *mb_bits;         // [F][nmb]  bit length of each macroblock's syntax
+    uint32_t *mb_off;          // [F][nmb]  bit offset inside its slice (slice header included)
+    uint32_t *slice_off;       // [F][mbh]  byte offset of slice inside the frame's slice area
+    uint32_t *frame_bytes;     // [F]       slice-area bytes of the frame
+    unsigned long long *frame_off; // [F+1] byte offset of each frame in the body; [F] = total
+    uint32_t *out_words;       // body, big-endian bit order packed into bytes
+};
+
+// K1: one warp per macroblock; step t = frame index inside every GOP of the batch
+void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st);
+// K2: one warp per macroblock; count = bit lengths only, write = emit into out_words
+void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st);
+// K3: slice/frame/batch scans of the bit lengths; then headers
+void m2v_launch_k3_scan(const M2VBatch &b, cudaStream_t st);
+void m2v_launch_headers(const M2VBatch &b, cudaStream_t st);
+// one-time upload of the VLC / quantiser tables for this Q_LEVEL
+cudaError_t m2v_upload_tables(int Q);

@@ -1,0 +1,165 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the oracle and the
+committed golden fixture.  Bit-exact: integer / byte work, tolerance 0."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _unpack(info):
+    inter = (info & 1).astype(np.int8)
+    mvx = ((info >> 8) & 0xFF).astype(np.uint8).view(np.int8)
+    mvy = ((info >> 16) & 0xFF).astype(np.uint8).view(np.int8)
+    cbp = ((info >> 24) & 63).astype(np.uint8)
+    return inter, mvx, mvy, cbp
+
+
+def _compare(pkg, ob, frames, P, VL=3, Q=2, XL=7, YL=7, partial_px4=0):
+    n, _, H, W = frames.shape
+    enc = pkg.Mpeg2Encoder(XL=XL, YL=YL, VECTOR_LEVEL=VL, Q_LEVEL=Q)
+    got = enc.encode_sequence(frames, P, partial_px4=partial_px4)
+    want, dbg = ob.encode(frames, W // 16, H // 16, P, XL=XL, YL=YL, VL=VL, Q=Q, partial_px4=partial_px4, want_dbg=True)
+    if got != want:
+        # localise: per-macroblock records and levels of the (single) batch
+        nmb = (W // 16) * (H // 16)
+        info, coefs = enc.debug_copy(n * nmb)
+        inter, mvx, mvy, cbp = _unpack(info)
+        msg = []
+        for name, a, b in (('inter', inter, dbg['mb_inter']), ('mvx', mvx, dbg['mb_mvx']), ('mvy', mvy, dbg['mb_mvy']),
+                           ('cbp', cbp, dbg['mb_cbp'])):
+            bad = np.nonzero(a != b)[0]
+            if bad.size:
+                i = int(bad[0])
+                msg.append('%s: %d diffs, first at frame %d mb %d: got %d want %d' % (name, bad.size, i // nmb, i % nmb, a[i], b[i]))
+        badc = np.nonzero((coefs != dbg['coefs']).any(axis=(1, 2)))[0]
+        if badc.size:
+            i = int(badc[0])
+            msg.append('coefs: %d mbs differ, first frame %d mb %d' % (badc.size, i // nmb, i % nmb))
+        first = next((i for i in range(min(len(got), len(want))) if got[i] != want[i]), None)
+        pytest.fail('stream mismatch: len %d vs %d, first byte diff %s; %s' % (len(got), len(want), first, '; '.join(msg)))
+    enc.close()
+    return got
+
+
+def test_golden_fixture(pkg, ob):
+    fr = np.fromfile(os.path.join(GOLD, 'clipA_64x64.yuv'), dtype=np.uint8).reshape(5, 3, 64, 64)
+    want = open(os.path.join(GOLD, 'clipA_64x64.m2v'), 'rb').read()
+    enc = pkg.Mpeg2Encoder(XL=7, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2)
+    assert enc.encode_sequence(fr, 23) == want
+
+
+def test_intra_only_config2_shape(pkg, ob, synth):
+    """config 2 shape (640x480, i_pframes_count=0) at a size the oracle finishes in seconds"""
+    _compare(pkg, ob, synth.s1_pan(20260927, 6, 640, 480), 0)
+
+
+@pytest.mark.parametrize('gen', ['S1', 'S2', 'S3', 'S4'])
+def test_clip_classes(pkg, ob, synth, gen):
+    fr = synth.GENERATORS[gen](20260925, 9, 160, 112)
+    _compare(pkg, ob, fr, 7)
+
+
+@pytest.mark.parametrize('VL', [1, 2, 3])
+@pytest.mark.parametrize('Q', [1, 2, 3, 4])
+def test_parameter_grid(pkg, ob, synth, VL, Q):
+    fr = np.concatenate([synth.s1_pan(VL * 10 + Q, 5, 96, 80), synth.s4_edges(VL * 10 + Q, 4, 96, 80)])
+    _compare(pkg, ob, fr, 3, VL=VL, Q=Q)
+
+
+@pytest.mark.parametrize('P', [0, 1, 7, 23, 255])
+def test_gop_lengths(pkg, ob, synth, P):
+    _compare(pkg, ob, synth.s1_pan(P + 1, 27, 64, 64), P)
+
+
+def test_mid_frame_stop_and_push4(pkg, ob, synth):
+    fr = synth.s1_pan(77, 4, 80, 64)
+    _compare(pkg, ob, fr, 7, partial_px4=333)
+    _compare(pkg, ob, fr[:1], 7, partial_px4=1)
+
+
+def test_push4_whole_frames_equals_bulk(pkg, synth):
+    fr = synth.s1_pan(5, 2, 64, 64)
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    a = enc.encode_sequence(fr, 3)
+    enc.begin(4, 4, 3)
+    for f in fr:
+        yy, uu, vv = f[0].reshape(-1), f[1].reshape(-1), f[2].reshape(-1)
+        for i in range(64 * 64 // 4):
+            enc.push4(yy[4 * i:4 * i + 4], uu[4 * i:4 * i + 4], vv[4 * i:4 * i + 4])
+    assert enc.sequence_busy
+    enc.sequence_stop()
+    b, last = enc.drain()
+    assert last and a == b and not enc.sequence_busy
+
+
+def test_back_to_back_sequences_and_clamp(pkg, ob, synth):
+    """the testbench's scenario (TB:150): several sequences on one instance; plus the size clamp"""
+    enc = pkg.Mpeg2Encoder(XL=4, YL=4, VECTOR_LEVEL=2, Q_LEVEL=3)
+    for seed, (W, H) in enumerate([(128, 64), (64, 96), (256, 256)]):
+        fr = synth.s1_pan(seed, 5, W, H)
+        assert enc.encode_sequence(fr, 2) == ob.encode(fr, W // 16, H // 16, 2, XL=4, YL=4, VL=2, Q=3)
+    assert enc.begin(100, 2, 0) == (16, 4)                   # clamp (RTL:985-991)
+    with pytest.raises(pkg.M2VError):
+        enc.push4([0] * 4, [0] * 4, [0] * 4); enc.begin(4, 4, 0)     # begin while busy
+    enc.sequence_stop(); enc.drain()
+
+
+def test_word_interface(pkg, ob, synth):
+    fr = synth.s1_pan(9, 3, 64, 64)
+    enc = pkg.Mpeg2Encoder()
+    enc.begin(4, 4, 1); enc.push_frames(fr); enc.sequence_stop()
+    words = []
+    while True:
+        w = enc.pull()
+        if w is None:
+            break
+        words.append(w)
+    assert [l for _, l in words] == [False] * (len(words) - 1) + [True]
+    assert b''.join(w for w, _ in words) == ob.encode(fr, 4, 4, 1, XL=6, YL=6)
+
+
+def test_gop_sharding_on_device(pkg, ob, synth):
+    """bodies of GOP ranges, encoded independently from device-resident frames, concatenate to the
+    whole-sequence stream (what bench.py --gpus N does across ranks)"""
+    import torch
+    from fpga_mpeg2_encoder_b200 import sharding
+    fr = synth.s1_pan(31, 22, 96, 64)
+    P = 3
+    d = torch.from_numpy(fr).cuda()
+    enc = pkg.Mpeg2Encoder(XL=7, YL=7)
+    fsz = fr[0].size
+    bodies = []
+    out = np.zeros(4 << 20, np.uint8)
+    for n0, n1 in sharding.gop_partition(22, P, 3):
+        ln = enc.encode_gops_host(d.data_ptr() + n0 * fsz, n1 - n0, n0, 6, 4, P, out)
+        bodies.append(out[:ln].tobytes())
+    got = pkg.finish_stream(pkg.sequence_header(6, 4) + b''.join(bodies))
+    assert got == ob.encode(fr, 6, 4, P, XL=7, YL=7)
+
+
+def test_config3_and_config4_sizes_sample_gop(pkg, ob, synth):
+    """full frame sizes of configs 3/4 (1280x720 I+7P, 1920x1152 I+15P): one short GOP each against
+    the oracle, plus size-independent properties on a longer run: idempotence and GOP locality."""
+    import torch
+    for (W, H, P, n) in ((1280, 720, 7, 3), (1920, 1152, 15, 3)):
+        fr = synth.s1_pan(W, n, W, H)
+        _compare(pkg, ob, fr, P)
+    W, H, P = 1920, 1152, 15
+    fr = synth.s1_pan_torch(4, 40, W, H, 'cuda')
+    enc = pkg.Mpeg2Encoder(XL=7, YL=7)
+    out = np.zeros(64 << 20, np.uint8)
+    la = enc.encode_gops_host(fr.data_ptr(), 40, 0, W // 16, H // 16, P, out)
+    a = out[:la].tobytes()
+    lb = enc.encode_gops_host(fr.data_ptr(), 40, 0, W // 16, H // 16, P, out)
+    assert a == out[:lb].tobytes()                                              # idempotent
+    fsz = 3 * W * H
+    l1 = enc.encode_gops_host(fr.data_ptr() + 16 * fsz, 16, 16, W // 16, H // 16, P, out)
+    mid = out[:l1].tobytes()
+    assert mid in a                                                             # GOP 1 is a contiguous, independent unit
+    host = fr[16:19].cpu().numpy()
+    want = ob.encode_range(host, 16, W // 16, H // 16, P)
+    l2 = enc.encode_gops_host(fr.data_ptr() + 16 * fsz, 3, 16, W // 16, H // 16, P, out)
+    assert out[:l2].tobytes() == want

@@ -1,0 +1,136 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every symbol include/m2venc.h
+declares (no compute calls without a GPU), framing helpers, the reciprocal-divide table, GOP
+partitioning, the world_size-2 gloo gather, and the synthetic generators."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_match_header(pkg):
+    hdr = open(os.path.join(ROOT, 'include', 'm2venc.h')).read()
+    declared = set(re.findall(r'\b(m2v_[a-z0-9_]+)\s*\(', hdr)) - {'m2v_encoder'}
+    assert declared == set(pkg.ABI_SYMBOLS)
+    L = pkg.lib()
+    for s in declared:
+        assert getattr(L, s) is not None
+    nm = subprocess.run(['nm', '-D', '--defined-only', pkg.LIB_PATH], capture_output=True, text=True).stdout
+    for s in declared:
+        assert re.search(r'\bT %s\b' % s, nm), s
+
+
+def test_no_cpu_fallback_without_gpu(pkg):
+    """the product must fail loudly when no B200 is present (no oracle / CPU fallback)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(pkg.M2VError) as ei:
+        pkg.Mpeg2Encoder()
+    assert ei.value.code == pkg.M2V_ENODEV
+    h = C.c_void_p()
+    assert pkg.lib().m2v_create(3, 6, 3, 2, C.byref(h)) == pkg.M2V_EINVAL     # parameter sets of RTL:11-14
+    assert pkg.lib().m2v_create(6, 6, 4, 2, C.byref(h)) == pkg.M2V_EINVAL
+    assert pkg.lib().m2v_create(6, 6, 3, 5, C.byref(h)) == pkg.M2V_EINVAL
+
+
+def test_product_does_not_reference_oracle():
+    pk = os.path.join(ROOT, 'fpga-mpeg2-encoder_b200')
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h', 'Makefile')):
+                txt = open(os.path.join(dp, f), errors='ignore').read()
+                assert 'oracle_binding' not in txt and 'm2v_oracle' not in txt and 'libm2v_oracle' not in txt, f
+
+
+def test_framing_helpers_match_oracle(pkg, ob):
+    for mbw, mbh in ((4, 4), (18, 13), (120, 72), (128, 128)):
+        assert pkg.sequence_header(mbw, mbh) == ob.seq_header(mbw, mbh)
+    for n in (34, 35, 60, 61, 62, 63, 64, 1000):
+        data = bytes(range(256)) * 4
+        out = pkg.finish_stream(data[:n])
+        assert len(out) == ob.lib().m2v_oracle_tail_len(n) and out[:n] == data[:n]
+        assert out[n:n + 4] == b'\x00\x00\x01\xb7' and not any(out[n + 4:])
+
+
+def test_reciprocal_division_is_exact():
+    """K1 replaces the intra-AC divide (RTL:2072) by umulhi(n, ceil(2^32/W)); exact for n < 2^15."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import gen_tables as G
+    n = np.arange(1 << 15, dtype=np.uint64)
+    for w in sorted(set(sum(G.INTRA_Q, []))):
+        r = np.uint64((0x100000000 + w - 1) // w)
+        assert ((n * r) >> np.uint64(32) == n // np.uint64(w)).all(), w
+
+
+def test_gop_partition(pkg):
+    from fpga_mpeg2_encoder_b200 import sharding
+    for nfr, P, world in ((512, 15, 8), (1000, 15, 8), (22, 3, 3), (5, 7, 4), (16, 0, 5)):
+        parts = sharding.gop_partition(nfr, P, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == nfr
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c
+        for a, b in parts:
+            assert a % (P + 1) == 0 or a == nfr
+    assert sharding.gop_partition(1000, 15, 8)[0] == (0, 128)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import __graft_entry__ as ge
+pkg = ge.load_package(); synth = ge.load_synth()
+from fpga_mpeg2_encoder_b200 import sharding
+import oracle_binding as ob
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+fr = synth.s1_pan(3, 10, 64, 64); P = 3
+n0, n1 = sharding.gop_partition(10, P, 2)[rank]
+# the encoder of a rank is injected: on the CPU box the oracle stands in for the CUDA library
+body = torch.frombuffer(bytearray(ob.encode_range(fr[n0:n1], n0, 4, 4, P)), dtype=torch.uint8)
+bodies = sharding.gather_bodies(body, dist)
+if rank == 0:
+    got = sharding.assemble_stream(pkg.sequence_header(4, 4), bodies, pkg.finish_stream)
+    assert got == ob.encode(fr, 4, 4, P), 'sharded stream differs'
+    print('OK', len(got))
+else:
+    assert bodies is None
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_gather(tmp_path):
+    """world_size 2 over gloo: GOP partition -> per-rank encode -> gather -> rank-0 concatenation is
+    byte-identical to the single-process stream."""
+    import socket
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'OK' in outs[0]
+
+
+def test_synth_is_deterministic(synth):
+    for name, gen in synth.GENERATORS.items():
+        a = gen(42, 3, 64, 48); b = gen(42, 3, 64, 48)
+        assert a.dtype == np.uint8 and a.shape == (3, 3, 48, 64) and (a == b).all(), name
+    assert (synth.s2_white(1, 2, 64, 48) != synth.s2_white(2, 2, 64, 48)).any()
+
+
+def test_tables_generator_is_current():
+    """the committed generated headers equal what tools/gen_tables.py emits; in the build container
+    they are also cross-checked against the RTL's tables"""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import gen_tables as G
+    assert open(os.path.join(ROOT, 'oracle', 'm2v_tables.h')).read() == G.emit('', 'M2V_ORACLE_TABLES_H', 'Oracle copy (test infrastructure).')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_tables_vs_rtl.py')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
