@@ -141,7 +141,8 @@ static int encode_chunk(m2v_encoder *e, int mbw, int mbh, int P, const uint8_t *
     b.g.mbw = mbw; b.g.mbh = mbh; b.g.W = mbw * 16; b.g.H = mbh * 16; b.g.nmb = mbw * mbh; b.g.P = P; b.g.VL = e->VL; b.g.Q = e->Q;
     b.F = F; b.n0 = n0; b.in = d_in;
     const long gop = P + 1, G = (F + gop - 1) / gop;
-    const size_t fsz420 = (size_t)b.g.W * b.g.H * 3 / 2, nmbF = (size_t)F * b.g.nmb;
+    b.CWp = ((b.g.W / 2) + 15) & ~15; b.fsz420 = (size_t)b.g.W * b.g.H + (size_t)2 * b.CWp * (b.g.H / 2);
+    const size_t fsz420 = b.fsz420, nmbF = (size_t)F * b.g.nmb;
     CK(e->d_recon0.reserve(G * fsz420)); CK(e->d_recon1.reserve(P ? G * fsz420 : 16));
     CK(e->d_coefs.reserve(nmbF * 384)); CK(e->d_mbinfo.reserve(nmbF)); CK(e->d_mb_bits.reserve(nmbF)); CK(e->d_mb_off.reserve(nmbF));
     CK(e->d_slice_off.reserve((size_t)F * mbh)); CK(e->d_frame_bytes.reserve(F)); CK(e->d_frame_off.reserve(F + 1));
@@ -149,6 +150,7 @@ static int encode_chunk(m2v_encoder *e, int mbw, int mbh, int P, const uint8_t *
     b.coefs = e->d_coefs.p; b.mbinfo = e->d_mbinfo.p; b.mb_bits = e->d_mb_bits.p; b.mb_off = e->d_mb_off.p;
     b.slice_off = e->d_slice_off.p; b.frame_bytes = e->d_frame_bytes.p; b.frame_off = e->d_frame_off.p; b.out_words = nullptr;
     e->last_F = F; e->last_nmb = b.g.nmb;
+    if (!m2v_make_tmaps(b)) { snprintf(e->err, sizeof e->err, "cuTensorMapEncodeTiled failed"); return M2V_ECUDA; }
 
     if (e->timing) CK(cudaEventRecord(e->ev[0], e->st));
     for (int t = 0; t <= P && t < F; t++) {                       // frame t of every GOP that has one

@@ -11,6 +11,7 @@
 // which lines each block reproduces.  All arithmetic is integer and must be bit-exact.
 #include "m2v_kernels.cuh"
 #include "m2v_tables.cuh"
+#include <cuda.h>
 #include <stdio.h>
 
 #define FULL 0xFFFFFFFFu
@@ -49,6 +50,12 @@ cudaError_t m2v_upload_tables(int) {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+// sum of 4 byte-wise |a-b| plus c in one instruction (VABSDIFF4.U8.ACC)
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 __device__ __forceinline__ uint32_t exlo(uint32_t v) { return __byte_perm(v, 0, 0x4140); }   // bytes 0,1 -> halfwords
 __device__ __forceinline__ uint32_t exhi(uint32_t v) { return __byte_perm(v, 0, 0x4342); }   // bytes 2,3 -> halfwords
@@ -129,78 +136,126 @@ __device__ __forceinline__ void idct_col(const int a[8], int o[8]) {
 // ------------------------------------------------------------------------------------------------
 #define K1_WARPS 8
 #define TSTR 72                      // padded tile stride (words) of the transform scratch
-struct __align__(16) WarpSmem {
-    uint32_t curY[16][4];            // current luma block, 16 rows x 16 B
+// One pipeline stage = everything TMA brings in for one macroblock.  Every member is a dense TMA box
+// and starts on a 128-byte boundary.
+struct __align__(128) StageSmem {
+    uint32_t curY[16][4];            // current luma block, 16 rows x 16 B                (box 16x16 of plane Y)
+    uint32_t curU[16][4];            // current 4:4:4 U block                             (box 16x16 of plane U)
+    uint32_t curV[16][4];            //                 V
+    uint32_t winC[2][16][4];         // chroma windows: rows 8by-4..8by+11, bytes 8bx-4..8bx+11   (2 boxes 16x16)
+    uint32_t winY[32][8];            // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-8..X0+23    (box 32 x (18+2R))
+};
+struct __align__(128) WarpSmem {
+    StageSmem st[2];                 // double buffer: TMA fills st[k^1] while st[k] is being encoded
     uint32_t curC[2][8][2];          // current 4:2:0 chroma blocks
-    uint32_t winY[30][8];            // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-8..X0+23
-    uint32_t winC[2][16][4];         // chroma windows: rows 8by-4..8by+11, bytes 8bx-4..8bx+11
     int16_t res[6][64];              // residual, later the zig-zag levels
     uint8_t pred[6][64];             // prediction, later the reconstruction
-    int32_t tmp[6 * TSTR];           // transform scratch
+    unsigned long long bar[2];       // one mbarrier per stage
 };
+// the transform scratch (4 tile slots x TSTR words) aliases winC+winY of the stage being encoded:
+// the windows are dead once the prediction has been formed.
+static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 4 + 32 * 8), "scratch must fit in the window area");
 
 struct K1Args {
-    const uint8_t *in; uint8_t *rec; const uint8_t *ref;   // rec/ref: [G][W*H*3/2]
+    uint8_t *rec;                                           // reconstruction out: [G][fsz420]
     int16_t *coefs; uint32_t *mbinfo;
-    int W, H, mbw, mbh, nmb, P, Q, t;
-    long total;                                             // ngops_t * nmb
+    int W, H, mbw, mbh, nmb, P, Q, t, CWp;                  // CWp = chroma row stride of the recon buffers (16-byte multiple)
+    unsigned fsz420;                                        // bytes per reconstructed frame = W*H + 2*CWp*H/2
+    unsigned total;                                         // ngops_t * nmb macroblocks in this launch
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+// Persistent warps: warp w encodes macroblocks w, w+nwarps, w+2*nwarps, ... of the launch; the TMA
+// loads of the next macroblock are in flight while the current one is encoded.
 template <int VL, bool PFRAME>
-__global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
+                                                               const __grid_constant__ CUtensorMap tm_refY,
+                                                               const __grid_constant__ CUtensorMap tm_refC) {
     constexpr int R = 2 * VL;
     constexpr int WROWS = 18 + 2 * R;
-    __shared__ WarpSmem smem[K1_WARPS];
+    constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 256 + 32 * WROWS : 0);
+    extern __shared__ unsigned char smem_raw[];
     __shared__ QEntry qt[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) qt[threadIdx.x] = d_qtab[p.Q - 1][threadIdx.x];
     __syncthreads();
-    const long gw = (long)blockIdx.x * K1_WARPS + warp;
-    if (gw >= p.total) return;
-    WarpSmem &s = smem[warp];
-    const int g = (int)(gw / p.nmb), mb = (int)(gw % p.nmb), by = mb / p.mbw, bx = mb % p.mbw;
+    WarpSmem &s = reinterpret_cast<WarpSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127)[warp];
+    const unsigned gwarp = blockIdx.x * K1_WARPS + warp, nwarps = gridDim.x * K1_WARPS;
+    if (gwarp >= p.total) return;
+    const int W = p.W, CWp = p.CWp;
+    const size_t ysz = (size_t)W * p.H;
+
+    // one elected lane arms the stage's mbarrier with the byte count and issues the TMA boxes
+    auto issue = [&](unsigned idx, int stg) {
+        const unsigned g = idx / (unsigned)p.nmb, mb = idx - g * p.nmb;
+        const int by = (int)(mb / (unsigned)p.mbw), bx = (int)mb - by * p.mbw;
+        const int n = (int)g * (p.P + 1) + p.t;
+        StageSmem &S = s.st[stg];
+        const uint32_t bar = smem_u32(&s.bar[stg]);
+        mbar_expect_tx(bar, TX_BYTES);
+        tma_load_4d(smem_u32(S.curY), &tm_in, bx * 16, by * 16, 0, n, bar);
+        tma_load_4d(smem_u32(S.curU), &tm_in, bx * 16, by * 16, 1, n, bar);
+        tma_load_4d(smem_u32(S.curV), &tm_in, bx * 16, by * 16, 2, n, bar);
+        if (PFRAME) {
+            // out-of-frame parts of a box are zero-filled by TMA; they only ever feed candidates the border
+            // rule disables (RTL:1642-1645, 1757-1760).  (RTL:1350-1425, 1613-1629 fetch the same windows.)
+            tma_load_3d(smem_u32(S.winY), &tm_refY, bx * 16 - 8, by * 16 - (R + 1), (int)g, bar);
+            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, bx * 8 - 4, by * 8 - 4, 0, (int)g, bar);
+            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, bx * 8 - 4, by * 8 - 4, 1, (int)g, bar);
+        }
+    };
+    if (lane == 0) {
+        mbar_init(smem_u32(&s.bar[0]), 1); mbar_init(smem_u32(&s.bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        issue(gwarp, 0);
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    int stg = 0;
+#pragma unroll 1
+    for (unsigned idx = gwarp; idx < p.total; idx += nwarps, stg ^= 1) {
+    if (lane == 0 && idx + nwarps < p.total) { fence_proxy_async(); issue(idx + nwarps, stg ^ 1); }
+    const unsigned g = idx / (unsigned)p.nmb, mb = idx - g * p.nmb;
+    const int by = (int)(mb / (unsigned)p.mbw), bx = (int)mb - by * p.mbw;
     const long n = (long)g * (p.P + 1) + p.t;               // frame index inside the batch
-    const int W = p.W, H = p.H, CW = W >> 1;
     const int Y0 = by * 16, X0 = bx * 16;
-    const size_t ysz = (size_t)W * H;
-    const uint8_t *fin = p.in + (size_t)n * 3 * ysz;
+    StageSmem &S = s.st[stg];
+    int32_t *const tmp = reinterpret_cast<int32_t *>(&S.winC[0][0][0]);
+    mbar_wait(smem_u32(&s.bar[stg]), (phase >> stg) & 1u);
+    phase ^= 1u << stg;
 
     // ---- current block: Y as is; U,V 4:4:4 -> 4:2:0 = mean2 of pixel pairs, then mean2 of the two
     //      horizontally subsampled rows (RTL:1086-1089, 1167-1170) -------------------------------
-    if (lane < 16) {
-        uint4 v = __ldg((const uint4 *)(fin + (size_t)(Y0 + lane) * W + X0));
-        *(uint4 *)s.curY[lane] = v;
-    }
     {
         const int comp = lane >> 4, r = lane & 15;
-        uint4 v = __ldg((const uint4 *)(fin + (1 + comp) * ysz + (size_t)(Y0 + r) * W + X0));
+        uint4 v = *(const uint4 *)(comp ? S.curV[r] : S.curU[r]);
         uint32_t h0 = __vavgu4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
         uint32_t h1 = __vavgu4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
         uint32_t g0 = __shfl_xor_sync(FULL, h0, 1), g1 = __shfl_xor_sync(FULL, h1, 1);
         if (!(r & 1)) { s.curC[comp][r >> 1][0] = __vavgu4(g0, h0); s.curC[comp][r >> 1][1] = __vavgu4(g1, h1); }
     }
-
-    int inter = 0, mvx = 0, mvy = 0;
-    if (PFRAME) {
-        // ---- reference windows (RTL:1350-1425, 1613-1629).  Out-of-frame bytes are zero; they only
-        //      ever feed candidates the border rule disables (RTL:1642-1645, 1757-1760). -----------
-        const uint8_t *rY = p.ref + (size_t)g * (ysz * 3 / 2);
-        for (int i = lane; i < WROWS * 4; i += 32) {
-            int r = i >> 2, seg = i & 3, yy = Y0 - (R + 1) + r, xx = X0 - 8 + seg * 8;
-            uint2 v = make_uint2(0, 0);
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *(const uint2 *)(rY + (size_t)yy * W + xx);
-            *(uint2 *)&s.winY[r][seg * 2] = v;
-        }
-        for (int i = lane; i < 128; i += 32) {
-            int comp = i >> 6, r = (i >> 2) & 15, seg = i & 3, yy = by * 8 - 4 + r, xx = bx * 8 - 4 + seg * 4;
-            uint32_t v = 0;
-            if (yy >= 0 && yy < (H >> 1) && xx >= 0 && xx < CW)
-                v = *(const uint32_t *)(rY + ysz + comp * (ysz >> 2) + (size_t)yy * CW + xx);
-            s.winC[comp][r][seg] = v;
-        }
-    }
     __syncwarp();
 
+    int inter = 0, mvx = 0, mvy = 0;
     if (PFRAME) {
         // ---- full-pel search (RTL:1634-1715).  lane = dxi + 16*half: candidate column dx = dxi-R,
         //      half = which 8 bytes of every 16-byte row.  Each lane keeps 2R+1 accumulators (one
@@ -211,21 +266,21 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
             int dxi = lane & 15; if (dxi > 2 * R) dxi = 2 * R;
             uint32_t cur[16][2];
 #pragma unroll
-            for (int y = 0; y < 16; y++) { cur[y][0] = s.curY[y][half * 2]; cur[y][1] = s.curY[y][half * 2 + 1]; }
+            for (int y = 0; y < 16; y++) { cur[y][0] = S.curY[y][half * 2]; cur[y][1] = S.curY[y][half * 2 + 1]; }
             uint32_t acc[2 * R + 1];
 #pragma unroll
             for (int i = 0; i <= 2 * R; i++) acc[i] = 0;
             const int o = 8 + (dxi - R) + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
 #pragma unroll
             for (int wr = 0; wr < 16 + 2 * R; wr++) {       // reference row Y0 - R + wr  = window row wr+1
-                uint32_t w0 = s.winY[wr + 1][wi], w1 = s.winY[wr + 1][wi + 1], w2 = s.winY[wr + 1][wi + 2];
+                uint32_t w0 = S.winY[wr + 1][wi], w1 = S.winY[wr + 1][wi + 1], w2 = S.winY[wr + 1][wi + 2];
                 uint32_t a = fsr(w0, w1, sh), b = fsr(w1, w2, sh);
 #pragma unroll
                 for (int dyi = 0; dyi <= 2 * R; dyi++) {
                     const int cy = wr - dyi;
                     if (cy >= 0 && cy < 16) {
-                        acc[dyi] = __vsadu4(a, cur[cy][0]) + acc[dyi];
-                        acc[dyi] = __vsadu4(b, cur[cy][1]) + acc[dyi];
+                        acc[dyi] = sad4(a, cur[cy][0], acc[dyi]);
+                        acc[dyi] = sad4(b, cur[cy][1], acc[dyi]);
                     }
                 }
             }
@@ -245,7 +300,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
 
         // ---- half-pel refinement + intra/inter decision (RTL:1743-1816).  lane = 2*y + half. ----
         const int y = lane >> 1, half = lane & 1;
-        const uint32_t c0 = s.curY[y][half * 2], c1 = s.curY[y][half * 2 + 1];
+        const uint32_t c0 = S.curY[y][half * 2], c1 = S.curY[y][half * 2 + 1];
         uint32_t cand[9][2];
         {
             const int wr0 = (R + 1) + fmvy + y - 1;
@@ -253,7 +308,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
             uint32_t zm[3][2], zz[3][2], zp[3][2];           // bytes x-1, x, x+1 of rows y-1,y,y+1
 #pragma unroll
             for (int rr = 0; rr < 3; rr++) {
-                const uint32_t *row = s.winY[wr0 + rr];
+                const uint32_t *row = S.winY[wr0 + rr];
                 uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2], w3 = row[min(wi + 3, 7)];
                 uint32_t v0 = fsr(w0, w1, sh), v1 = fsr(w1, w2, sh), v2 = fsr(w2, w3, sh);
                 zm[rr][0] = v0; zm[rr][1] = v1;
@@ -287,16 +342,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
             const bool yn = (by == 0 || fmvy == -R), yp = (by == p.mbh - 1 || fmvy == R);
 #pragma unroll
             for (int i = 0; i < 9; i++) {
-                uint32_t sd = __vsadu4(cand[i][0], c0) + __vsadu4(cand[i][1], c1);
+                uint32_t sd = sad4(cand[i][0], c0, sad4(cand[i][1], c1, 0));
                 sd = __reduce_add_sync(FULL, sd);
                 const int cy = i / 3 - 1, cx = i % 3 - 1;
                 bool dis = (cx < 0 && xn) || (cx > 0 && xp) || (cy < 0 && yn) || (cy > 0 && yp);   // RTL:1757-1760
                 key[i] = (dis || sd >= 4096u) ? 8191 : (int)sd;
             }
             // intra key: pixel sum + sum|pixel-mean|, 16 bit, saturated to 4095 (RTL:1600,1662,1744,1776-1777,1791)
-            uint32_t S = __reduce_add_sync(FULL, __vsadu4(c0, 0) + __vsadu4(c1, 0));
+            uint32_t S = __reduce_add_sync(FULL, sad4(c0, 0, sad4(c1, 0, 0)));
             uint32_t m = (S >> 8) & 0xFF; m |= m << 8; m |= m << 16;
-            uint32_t D = __reduce_add_sync(FULL, __vsadu4(c0, m) + __vsadu4(c1, m));
+            uint32_t D = __reduce_add_sync(FULL, sad4(c0, m, sad4(c1, m, 0)));
             uint32_t T = (S + D) & 0xFFFF;
             key[9] = T < 4096u ? (int)T : 4095;
         }
@@ -328,8 +383,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
                 const int cyv = mvy >> 1, cxv = mvx >> 1;          // floor (RTL:1904-1910)
                 const int fy = cyv >> 1, fx = cxv >> 1, oy = cyv & 1, ox = cxv & 1;
                 const int row = 4 + cyy + fy, o = 4 + 4 * ch + fx, wi = o >> 2, sh = (o & 3) * 8;
-                unsigned long long t0 = ((unsigned long long)s.winC[comp][row][wi + 1] << 32 | s.winC[comp][row][wi]) >> sh;
-                unsigned long long t1 = ((unsigned long long)s.winC[comp][row + 1][wi + 1] << 32 | s.winC[comp][row + 1][wi]) >> sh;
+                unsigned long long t0 = ((unsigned long long)S.winC[comp][row][wi + 1] << 32 | S.winC[comp][row][wi]) >> sh;
+                unsigned long long t1 = ((unsigned long long)S.winC[comp][row + 1][wi + 1] << 32 | S.winC[comp][row + 1][wi]) >> sh;
                 uint32_t a0 = (uint32_t)t0, a1 = (uint32_t)(t0 >> 8), b0 = (uint32_t)t1, b1 = (uint32_t)(t1 >> 8);
                 if (oy && ox) {
                     uint32_t lo = exlo(a0) + exlo(a1) + exlo(b0) + exlo(b1), hi = exhi(a0) + exhi(a1) + exhi(b0) + exhi(b1);
@@ -345,7 +400,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
     } else {
         // I-frame: every macroblock intra, predictor 128, vector 0 (RTL:1820-1825, 1894-1903)
         const int y = lane >> 1, half = lane & 1;
-        const uint32_t c0 = s.curY[y][half * 2], c1 = s.curY[y][half * 2 + 1], pz = 0x80808080u;
+        const uint32_t c0 = S.curY[y][half * 2], c1 = S.curY[y][half * 2 + 1], pz = 0x80808080u;
         const int tile = (y >> 3) * 2 + half, r = y & 7;
         *(uint2 *)&s.pred[tile][r * 8] = make_uint2(pz, pz);
         uint4 rv;
@@ -368,7 +423,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
     for (int round = 0; round < 2; round++) {
         const bool act = (round == 0) || lane < 16;
         const int tile = round * 4 + (lane >> 3), v = lane & 7;
-        int32_t *tt = s.tmp + tile * TSTR;
+        int32_t *tt = tmp + (lane >> 3) * TSTR;
         int x[8], o[8];
         if (act) {                                               // rows: A = R * DCTM^T (RTL:2029-2036)
             uint4 rv = *(const uint4 *)&s.res[tile][v * 8];
@@ -384,24 +439,40 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
             fdct8(x, o);
+            const int b00 = o[0];
+            // |C| <= 255*512*512/4096 = 16320, so every level is < 2047 and the RTL's clip (RTL:2075) never
+            // acts; the branch on `inter` is warp-uniform and hoisted out of the coefficient loop.
+            if (inter) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const QEntry qe = qt[i * 8 + v];
-                const int C = (o[i] + 2048) >> 12;                                   // RTL:2058
-                const uint32_t a = (uint32_t)abs(C);
-                uint32_t yq;
-                if (inter) yq = (a + 2) >> (4 + Q);                                  // RTL:2070
-                else if (i | v) yq = __umulhi((a + qe.off) >> Q, qe.recip);          // RTL:2072 (exact division)
-                else yq = (a >> 4) + ((a >> 3) & 1);                                 // RTL:2074
-                yq = min(yq, 2047u);                                                 // RTL:2075
-                const int q = C < 0 ? -(int)yq : (int)yq;
-                s.res[tile][qe.zz] = (int16_t)q;                                     // zig-zag (RTL:2464)
-                nzl |= (q != 0);
-                int xq;                                                              // dequantise (RTL:2132-2147)
-                if (inter) { xq = 2 * q + (q > 0) - (q < 0); xq <<= Q; xq = max(-2047, min(2047, xq)); }
-                else if (i | v) { xq = q * (int)qe.W; xq = (Q >= 3) ? (xq << (Q - 3)) : (xq >> (3 - Q)); xq = max(-2047, min(2047, xq)); }
-                else xq = 2 * q;
-                o[i] = xq;
+                for (int i = 0; i < 8; i++) {
+                    const int C = (o[i] + 2048) >> 12;                               // RTL:2058
+                    const int yq = (abs(C) + 2) >> (4 + Q);                          // RTL:2070
+                    const int q = C < 0 ? -yq : yq;
+                    s.res[tile][qt[i * 8 + v].zz] = (int16_t)q;                      // zig-zag (RTL:2464)
+                    nzl |= (yq != 0);
+                    const int m = min(yq ? ((2 * yq + 1) << Q) : 0, 2047);           // RTL:2134-2137
+                    o[i] = C < 0 ? -m : m;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const QEntry qe = qt[i * 8 + v];
+                    const int C = (o[i] + 2048) >> 12;
+                    const int yq = (int)__umulhi((uint32_t)(abs(C) + (int)qe.off) >> Q, qe.recip);   // RTL:2072 (exact division)
+                    const int q = C < 0 ? -yq : yq;
+                    s.res[tile][qe.zz] = (int16_t)q;
+                    int xq = q * (int)qe.W;                                          // RTL:2139-2144, >>> = floor
+                    xq = (Q >= 3) ? (xq << (Q - 3)) : (xq >> (3 - Q));
+                    o[i] = max(-2047, min(2047, xq));
+                }
+                if (v == 0) {                                                        // DC (RTL:2074, 2146)
+                    const int C = (b00 + 2048) >> 12, a = abs(C);
+                    const int yq = (a >> 4) + ((a >> 3) & 1);
+                    const int q = C < 0 ? -yq : yq;
+                    s.res[tile][0] = (int16_t)q;
+                    o[0] = 2 * q;
+                }
+                nzl = true;
             }
         }
         __syncwarp();                                            // all column reads of A done before overwrite
@@ -436,12 +507,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
 
     // ---- outputs: reconstruction (next frame's reference), levels, record -----------------------
     {
-        uint8_t *oY = p.rec + (size_t)g * (ysz * 3 / 2);
+        uint8_t *oY = p.rec + (size_t)g * p.fsz420;
         const int y = lane >> 1, half = lane & 1, tile = (y >> 3) * 2 + half;
         *(uint2 *)(oY + (size_t)(Y0 + y) * W + X0 + 8 * half) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
         if (lane < 16) {
             const int comp = lane >> 3, cyy = lane & 7;
-            *(uint2 *)(oY + ysz + comp * (ysz >> 2) + (size_t)(by * 8 + cyy) * CW + bx * 8) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
+            *(uint2 *)(oY + ysz + (size_t)comp * CWp * (p.H >> 1) + (size_t)(by * 8 + cyy) * CWp + bx * 8) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
         }
         const size_t mbi = (size_t)n * p.nmb + mb;
         uint2 *dst = (uint2 *)(p.coefs + mbi * 384);
@@ -450,20 +521,83 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p) {
         for (int k = 0; k < 3; k++) dst[lane + 32 * k] = src[lane + 32 * k];
         if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
     }
+    __syncwarp();
+    }   // persistent loop
+}
+
+// TMA descriptors for one batch: the 4:4:4 input [F][3][H][W], and per reconstruction buffer the luma
+// planes [G][H][W] and the chroma planes [G][2][H/2][CWp].  cuTensorMapEncodeTiled is fetched through the
+// runtime so that the library does not link against libcuda directly.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+static bool make_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool m2v_make_tmaps(M2VBatch &b) {
+    const cuuint64_t W = b.g.W, H = b.g.H, ysz = W * H, CWp = b.CWp, CH = H / 2, G = (b.F + b.g.P) / (b.g.P + 1);
+    const int WROWS = 18 + 4 * b.g.VL;
+    {
+        const cuuint64_t d[4] = {W, H, 3, (cuuint64_t)b.F}, st[3] = {W, ysz, 3 * ysz};
+        const cuuint32_t box[4] = {16, 16, 1, 1};
+        if (!make_map(&b.tm_in, (void *)b.in, 4, d, st, box)) return false;
+    }
+    for (int k = 0; k < 2; k++) {
+        const cuuint64_t dy[3] = {W, H, G}, sy[2] = {W, b.fsz420};
+        const cuuint32_t boxy[3] = {32, (cuuint32_t)WROWS, 1};
+        if (!make_map(&b.tm_refY[k], b.recon[k], 3, dy, sy, boxy)) return false;
+        const cuuint64_t dc[4] = {CWp, CH, 2, G}, sc[3] = {CWp, CWp * CH, b.fsz420};
+        const cuuint32_t boxc[4] = {16, 16, 1, 1};
+        if (!make_map(&b.tm_refC[k], b.recon[k] + ysz, 4, dc, sc, boxc)) return false;
+    }
+    return true;
+}
+
+static int k1_grid_cap = 0;
+template <int VL, bool PF>
+static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream_t st) {
+    const size_t smem = sizeof(WarpSmem) * K1_WARPS + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    if (!k1_grid_cap) {
+        int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        k1_grid_cap = sms * 4;                                     // 4 resident CTAs of 8 warps per SM (shared-memory bound)
+    }
+    unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
+    if (grid > (unsigned)k1_grid_cap) grid = k1_grid_cap;
+    k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, smem, st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
 }
 
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
     K1Args a;
-    a.in = b.in; a.rec = b.recon[t & 1]; a.ref = b.recon[(t & 1) ^ 1];
+    a.rec = b.recon[t & 1];
     a.coefs = b.coefs; a.mbinfo = b.mbinfo;
     a.W = b.g.W; a.H = b.g.H; a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.Q = b.g.Q; a.t = t;
-    a.total = ngops_t * b.g.nmb;
-    const unsigned grid = (unsigned)((a.total + K1_WARPS - 1) / K1_WARPS);
-    if (t == 0) { k1_mb_encode<1, false><<<grid, K1_WARPS * 32, 0, st>>>(a); return; }
+    a.CWp = b.CWp; a.fsz420 = (unsigned)b.fsz420;
+    a.total = (unsigned)(ngops_t * b.g.nmb);
+    const int refk = (t & 1) ^ 1;
+    if (t == 0) { launch_k1_t<1, false>(a, b, refk, st); return; }
     switch (b.g.VL) {
-        case 1: k1_mb_encode<1, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
-        case 2: k1_mb_encode<2, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
-        default: k1_mb_encode<3, true><<<grid, K1_WARPS * 32, 0, st>>>(a); break;
+        case 1: launch_k1_t<1, true>(a, b, refk, st); break;
+        case 2: launch_k1_t<2, true>(a, b, refk, st); break;
+        default: launch_k1_t<3, true>(a, b, refk, st); break;
     }
 }
 
@@ -551,9 +685,12 @@ __global__ void __launch_bounds__(256) k2_vlc(K2Args p) {
     }
     // ---- tiles (RTL:2777-2847).  lane L owns scan positions L and L+32. ----
     int prev_dc = 0;
-#pragma unroll 1
+    int lv0[6], lv1[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) { lv0[t] = zz[t * 64 + lane]; lv1[t] = zz[t * 64 + 32 + lane]; }
+#pragma unroll
     for (int t = 0; t < 6; t++) {
-        const int v0 = zz[t * 64 + lane], v1 = zz[t * 64 + 32 + lane];
+        const int v0 = lv0[t], v1 = lv1[t];
         const int dc = __shfl_sync(FULL, v0, 0);
         const int comp = t < 4 ? 0 : t - 3;
         const int pred = (t >= 1 && t <= 3) ? prev_dc : dcp[comp];

@@ -1,6 +1,7 @@
 // m2v_kernels.cuh - launch interface between the host state machine (m2v_host.cu) and the
 // sm_100a kernels (m2v_kernels.cu).  Product code; nothing here touches oracle/.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,7 +21,9 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     long F;                    // frames in the batch
     long n0;                   // absolute index of the first frame (GOP aligned)
     const uint8_t *in;         // [F][3][H][W] planar yuv444p (device)
-    uint8_t *recon[2];         // ping-pong reconstruction, each [G][W*H*3/2] (device)
+    uint8_t *recon[2];         // ping-pong reconstruction, each [G][fsz420]: Y W*H, then U and V with row stride CWp
+    int CWp; size_t fsz420;    // CWp = W/2 rounded up to 16 (TMA needs 16-byte strides); fsz420 = W*H + 2*CWp*H/2
+    CUtensorMap tm_in, tm_refY[2], tm_refC[2];   // TMA descriptors (m2v_make_tmaps)
     int16_t *coefs;            // [F][nmb][6][64] quantised levels, zig-zag order
     uint32_t *mbinfo;          // [F][nmb]
     uint32_t *mb_bits;         // [F][nmb]  bit length of each macroblock's syntax
@@ -31,6 +34,7 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     uint32_t *out_words;       // body, big-endian bit order packed into bytes
 };
 
+bool m2v_make_tmaps(M2VBatch &b);
 // K1: one warp per macroblock; step t = frame index inside every GOP of the batch
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st);
 // K2: one warp per macroblock; count = bit lengths only, write = emit into out_words

@@ -6,6 +6,8 @@
 #include <stdio.h>
 
 #define ITERS 4096
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 template <int OP>
 __global__ void k(uint32_t *out, uint32_t seed) {
     uint32_t a0 = threadIdx.x * 0x01010101u + seed, a1 = a0 ^ 0x55aa55aau, a2 = a0 + 0x01020304u, a3 = ~a0;
@@ -17,7 +19,7 @@ __global__ void k(uint32_t *out, uint32_t seed) {
     for (int i = 0; i < ITERS; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            if (OP == 0) { c0 = __vsadu4(a0, b) + c0; c1 = __vsadu4(a1, b) + c1; c2 = __vsadu4(a2, b) + c2; c3 = __vsadu4(a3, b) + c3; }
+            if (OP == 0) { c0 = sad4(a0, c1, c0); c1 = sad4(a1, c2, c1); c2 = sad4(a2, c3, c2); c3 = sad4(a3, c0, c3); }
             if (OP == 1) { c0 = __vavgu4(c0, a0); c1 = __vavgu4(c1, a1); c2 = __vavgu4(c2, a2); c3 = __vavgu4(c3, a3); }
             if (OP == 2) { c0 = __funnelshift_r(c0, a0, b); c1 = __funnelshift_r(c1, a1, b); c2 = __funnelshift_r(c2, a2, b); c3 = __funnelshift_r(c3, a3, b); }
             if (OP == 3) { c0 = __byte_perm(c0, a0, b); c1 = __byte_perm(c1, a1, b); c2 = __byte_perm(c2, a2, b); c3 = __byte_perm(c3, a3, b); }
