@@ -157,17 +157,20 @@ class Mpeg2Encoder:
         return (bytes(w), bool(last.value)) if rc == 1 else None
 
     def drain(self, cap=1 << 24):
-        out = bytearray()
+        """all available whole words -> (bytes, last)"""
+        chunks = []
         last = False
-        buf = (C.c_uint8 * cap)()
+        if getattr(self, '_drain_buf', None) is None or self._drain_buf.size < cap:
+            self._drain_buf = np.empty(cap, np.uint8)
+        buf = self._drain_buf
         while True:
             n = C.c_size_t(0); l = C.c_int(0)
-            self._ck(lib().m2v_drain(self._h, buf, cap, C.byref(n), C.byref(l)))
-            out += bytes(buf[:n.value])
+            self._ck(lib().m2v_drain(self._h, buf.ctypes.data, cap, C.byref(n), C.byref(l)))
+            chunks.append(buf[:n.value].tobytes())
             last = last or bool(l.value)
             if n.value < cap // 32 * 32:
                 break
-        return bytes(out), last
+        return b''.join(chunks), last
 
     def encode_sequence(self, frames, i_pframes_count, partial_px4=0):
         """Replay of the testbench stimulus (TB:206-266) for one sequence: frames [n,3,H,W] uint8

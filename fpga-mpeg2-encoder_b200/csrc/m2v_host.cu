@@ -52,7 +52,8 @@ struct m2v_encoder {
     long batch_frames = 0;             // flush threshold (whole GOPs)
     std::vector<uint8_t> outq; size_t out_rd = 0;
     // device buffers
-    DevBuf<uint8_t> d_in, d_recon0, d_recon1, d_body;
+    DevBuf<uint8_t> d_in, d_in2, d_recon0, d_recon1, d_body;
+    cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     DevBuf<int16_t> d_coefs;
     DevBuf<uint32_t> d_mbinfo, d_mb_bits, d_mb_off, d_slice_off, d_frame_bytes, d_out;
     DevBuf<unsigned long long> d_frame_off;
@@ -82,6 +83,8 @@ extern "C" int m2v_create(int XL, int YL, int VL, int Q, m2v_encoder **out) {
         delete e; return M2V_ECUDA;
     }
     for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
+    cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
     *out = e;
     return M2V_OK;
 }
@@ -91,7 +94,9 @@ extern "C" void m2v_destroy(m2v_encoder *e) {
     cudaSetDevice(e->dev);
     if (e->st) { cudaStreamSynchronize(e->st); cudaStreamDestroy(e->st); }
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-    e->d_in.release(); e->d_recon0.release(); e->d_recon1.release(); e->d_body.release(); e->d_coefs.release();
+    if (e->st_copy) cudaStreamDestroy(e->st_copy);
+    for (int i = 0; i < 2; i++) if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
+    e->d_in.release(); e->d_in2.release(); e->d_recon0.release(); e->d_recon1.release(); e->d_body.release(); e->d_coefs.release();
     e->d_mbinfo.release(); e->d_mb_bits.release(); e->d_mb_off.release(); e->d_slice_off.release();
     e->d_frame_bytes.release(); e->d_out.release(); e->d_frame_off.release();
     delete e;
@@ -255,9 +260,9 @@ extern "C" int m2v_begin(m2v_encoder *e, int xs, int ys, int P, int *mbw, int *m
     if (mbw) *mbw = e->mbw; if (mbh) *mbh = e->mbh;
     e->frames_encoded = 0; e->staged_frames = 0; e->px_in_frame = 0; e->ended = false;
     e->stage.clear(); e->outq.clear(); e->out_rd = 0;
-    // flush threshold: enough GOPs that one K1 step has >= 64k macroblocks, staging <= 1 GiB
+    // flush threshold: enough GOPs that one K1 step has >= 32k macroblocks, staging <= 1 GiB
     const long gop = P + 1, nmb = (long)e->mbw * e->mbh;
-    long g = (65536 + nmb - 1) / nmb;
+    long g = (32768 + nmb - 1) / nmb;
     const size_t fsz = (size_t)nmb * 768;
     while (g > 1 && (size_t)g * gop * fsz > ((size_t)1 << 30)) g--;
     e->batch_frames = g * gop;
@@ -315,19 +320,31 @@ extern "C" int m2v_push_frames(m2v_encoder *e, const uint8_t *yuv, long nframes)
     if (e->ended) { snprintf(e->err, sizeof e->err, "push after stop"); return M2V_ESTATE; }
     if (e->px_in_frame) { snprintf(e->err, sizeof e->err, "push_frames inside a frame"); return M2V_ESTATE; }
     const size_t fsz = (size_t)e->mbw * e->mbh * 768;
-    // whole batches go straight from the caller's buffer to HBM (no host staging copy)
-    while (e->staged_frames == 0 && nframes >= e->batch_frames) {
+    // whole batches go straight from the caller's buffer to HBM (no host staging copy), double
+    // buffered: the H2D copy of batch i+1 (copy stream) overlaps the kernels of batch i.
+    if (e->staged_frames == 0 && nframes >= e->batch_frames) {
         CK(cudaSetDevice(e->dev));
         const size_t bytes = fsz * e->batch_frames;
-        CK(e->d_in.reserve(bytes));
-        CK(cudaMemcpyAsync(e->d_in.p, yuv, bytes, cudaMemcpyHostToDevice, e->st));
-        const uint8_t *d = nullptr; size_t len = 0;
-        rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, e->d_in.p, e->batch_frames, e->frames_encoded, &d, &len);
-        if (rc) return rc;
-        const size_t at = e->outq.size();
-        e->outq.resize(at + len);
-        CK(cudaMemcpy(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost));
-        e->frames_encoded += e->batch_frames; yuv += bytes; nframes -= e->batch_frames;
+        CK(e->d_in.reserve(bytes)); CK(e->d_in2.reserve(bytes));
+        uint8_t *dbuf[2] = {e->d_in.p, e->d_in2.p};
+        const long nb = nframes / e->batch_frames;
+        CK(cudaMemcpyAsync(dbuf[0], yuv, bytes, cudaMemcpyHostToDevice, e->st_copy));
+        CK(cudaEventRecord(e->ev_copy[0], e->st_copy));
+        for (long i = 0; i < nb; i++) {
+            if (i + 1 < nb) {
+                CK(cudaMemcpyAsync(dbuf[(i + 1) & 1], yuv + (size_t)(i + 1) * bytes, bytes, cudaMemcpyHostToDevice, e->st_copy));
+                CK(cudaEventRecord(e->ev_copy[(i + 1) & 1], e->st_copy));
+            }
+            CK(cudaStreamWaitEvent(e->st, e->ev_copy[i & 1], 0));
+            const uint8_t *d = nullptr; size_t len = 0;
+            rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, dbuf[i & 1], e->batch_frames, e->frames_encoded, &d, &len);
+            if (rc) return rc;
+            const size_t at = e->outq.size();
+            e->outq.resize(at + len);
+            CK(cudaMemcpy(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost));
+            e->frames_encoded += e->batch_frames;
+        }
+        yuv += (size_t)nb * bytes; nframes -= nb * e->batch_frames;
     }
     while (nframes > 0) {
         const long take = std::min(nframes, e->batch_frames - e->staged_frames);

@@ -142,8 +142,10 @@ struct __align__(128) StageSmem {
     uint32_t curY[16][4];            // current luma block, 16 rows x 16 B                (box 16x16 of plane Y)
     uint32_t curU[16][4];            // current 4:4:4 U block                             (box 16x16 of plane U)
     uint32_t curV[16][4];            //                 V
-    uint32_t winC[2][16][4];         // chroma windows: rows 8by-4..8by+11, bytes 8bx-4..8bx+11   (2 boxes 16x16)
-    uint32_t winY[32][8];            // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-8..X0+23    (box 32 x (18+2R))
+    // TMA needs the inner coordinate of a box to be a multiple of 16 bytes (probed: tools/tma_probe.cu),
+    // so the windows start at the 16-byte boundary at or below the first byte that is needed.
+    uint32_t winC[2][16][8];         // chroma windows: rows 8by-4..8by+11, 32 bytes from (8bx-8)&~15     (2 boxes 32x16)
+    uint32_t winY[32][12];           // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-16..X0+31           (box 48 x (18+2R))
 };
 struct __align__(128) WarpSmem {
     StageSmem st[2];                 // double buffer: TMA fills st[k^1] while st[k] is being encoded
@@ -154,7 +156,7 @@ struct __align__(128) WarpSmem {
 };
 // the transform scratch (4 tile slots x TSTR words) aliases winC+winY of the stage being encoded:
 // the windows are dead once the prediction has been formed.
-static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 4 + 32 * 8), "scratch must fit in the window area");
+static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratch must fit in the window area");
 
 struct K1Args {
     uint8_t *rec;                                           // reconstruction out: [G][fsz420]
@@ -186,12 +188,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm,
 // Persistent warps: warp w encodes macroblocks w, w+nwarps, w+2*nwarps, ... of the launch; the TMA
 // loads of the next macroblock are in flight while the current one is encoded.
 template <int VL, bool PFRAME>
-__global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
+__global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
                                                                const __grid_constant__ CUtensorMap tm_refY,
                                                                const __grid_constant__ CUtensorMap tm_refC) {
     constexpr int R = 2 * VL;
     constexpr int WROWS = 18 + 2 * R;
-    constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 256 + 32 * WROWS : 0);
+    constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 512 + 48 * WROWS : 0);
     extern __shared__ unsigned char smem_raw[];
     __shared__ QEntry qt[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -217,9 +219,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __
         if (PFRAME) {
             // out-of-frame parts of a box are zero-filled by TMA; they only ever feed candidates the border
             // rule disables (RTL:1642-1645, 1757-1760).  (RTL:1350-1425, 1613-1629 fetch the same windows.)
-            tma_load_3d(smem_u32(S.winY), &tm_refY, bx * 16 - 8, by * 16 - (R + 1), (int)g, bar);
-            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, bx * 8 - 4, by * 8 - 4, 0, (int)g, bar);
-            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, bx * 8 - 4, by * 8 - 4, 1, (int)g, bar);
+            const int cx0 = (bx * 8 - 8) & ~15;
+            tma_load_3d(smem_u32(S.winY), &tm_refY, bx * 16 - 16, by * 16 - (R + 1), (int)g, bar);
+            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, by * 8 - 4, 0, (int)g, bar);
+            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, cx0, by * 8 - 4, 1, (int)g, bar);
         }
     };
     if (lane == 0) {
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __
             uint32_t acc[2 * R + 1];
 #pragma unroll
             for (int i = 0; i <= 2 * R; i++) acc[i] = 0;
-            const int o = 8 + (dxi - R) + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
+            const int o = 16 + (dxi - R) + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
 #pragma unroll
             for (int wr = 0; wr < 16 + 2 * R; wr++) {       // reference row Y0 - R + wr  = window row wr+1
                 uint32_t w0 = S.winY[wr + 1][wi], w1 = S.winY[wr + 1][wi + 1], w2 = S.winY[wr + 1][wi + 2];
@@ -304,12 +307,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __
         uint32_t cand[9][2];
         {
             const int wr0 = (R + 1) + fmvy + y - 1;
-            const int o = 7 + fmvx + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
+            const int o = 15 + fmvx + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
             uint32_t zm[3][2], zz[3][2], zp[3][2];           // bytes x-1, x, x+1 of rows y-1,y,y+1
 #pragma unroll
             for (int rr = 0; rr < 3; rr++) {
                 const uint32_t *row = S.winY[wr0 + rr];
-                uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2], w3 = row[min(wi + 3, 7)];
+                uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2], w3 = row[wi + 3];
                 uint32_t v0 = fsr(w0, w1, sh), v1 = fsr(w1, w2, sh), v2 = fsr(w2, w3, sh);
                 zm[rr][0] = v0; zm[rr][1] = v1;
                 zz[rr][0] = fsr(v0, v1, 8); zz[rr][1] = fsr(v1, v2, 8);
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_mb_encode(K1Args p, const __
             if (inter) {
                 const int cyv = mvy >> 1, cxv = mvx >> 1;          // floor (RTL:1904-1910)
                 const int fy = cyv >> 1, fx = cxv >> 1, oy = cyv & 1, ox = cxv & 1;
-                const int row = 4 + cyy + fy, o = 4 + 4 * ch + fx, wi = o >> 2, sh = (o & 3) * 8;
+                const int row = 4 + cyy + fy, o = ((bx & 1) ? 8 : 16) + 4 * ch + fx, wi = o >> 2, sh = (o & 3) * 8;
                 unsigned long long t0 = ((unsigned long long)S.winC[comp][row][wi + 1] << 32 | S.winC[comp][row][wi]) >> sh;
                 unsigned long long t1 = ((unsigned long long)S.winC[comp][row + 1][wi + 1] << 32 | S.winC[comp][row + 1][wi]) >> sh;
                 uint32_t a0 = (uint32_t)t0, a1 = (uint32_t)(t0 >> 8), b0 = (uint32_t)t1, b1 = (uint32_t)(t1 >> 8);
@@ -558,10 +561,10 @@ bool m2v_make_tmaps(M2VBatch &b) {
     }
     for (int k = 0; k < 2; k++) {
         const cuuint64_t dy[3] = {W, H, G}, sy[2] = {W, b.fsz420};
-        const cuuint32_t boxy[3] = {32, (cuuint32_t)WROWS, 1};
+        const cuuint32_t boxy[3] = {48, (cuuint32_t)WROWS, 1};
         if (!make_map(&b.tm_refY[k], b.recon[k], 3, dy, sy, boxy)) return false;
         const cuuint64_t dc[4] = {CWp, CH, 2, G}, sc[3] = {CWp, CWp * CH, b.fsz420};
-        const cuuint32_t boxc[4] = {16, 16, 1, 1};
+        const cuuint32_t boxc[4] = {32, 16, 1, 1};
         if (!make_map(&b.tm_refC[k], b.recon[k] + ysz, 4, dc, sc, boxc)) return false;
     }
     return true;
@@ -578,7 +581,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
     }
     if (!k1_grid_cap) {
         int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        k1_grid_cap = sms * 4;                                     // 4 resident CTAs of 8 warps per SM (shared-memory bound)
+        k1_grid_cap = sms * 3;                                     // 3 resident CTAs of 8 warps per SM (shared-memory bound)
     }
     unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
     if (grid > (unsigned)k1_grid_cap) grid = k1_grid_cap;
