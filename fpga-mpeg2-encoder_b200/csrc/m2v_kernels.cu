@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     constexpr int R = 2 * VL;
     constexpr int WROWS = 18 + 2 * R;
     constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 512 + 48 * WROWS : 0);
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];     // keeps the .shared address space: LDS/STS, not generic LD/ST
     __shared__ QEntry qt[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) qt[threadIdx.x] = d_qtab[p.Q - 1][threadIdx.x];
     __syncthreads();
-    WarpSmem &s = reinterpret_cast<WarpSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127)[warp];
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
     const unsigned gwarp = blockIdx.x * K1_WARPS + warp, nwarps = gridDim.x * K1_WARPS;
     if (gwarp >= p.total) return;
     const int W = p.W, CWp = p.CWp;

@@ -62,11 +62,18 @@ def main():
                     seq.append((line, m.group(2).strip()))
     src = open(SRC).read().split('\n')
     banners = [(i + 1, l.strip()[8:70]) for i, l in enumerate(src) if l.strip().startswith('// ---- ')]
+    first_banner = banners[0][0] if banners else 0
+    state = {'last': 'prologue'}
     def region(ln):
-        name = 'helpers / prologue'
+        # inlined helpers (defined above the first banner) carry their own line numbers; attribute them
+        # to the region of the nearest preceding instruction that belongs to the kernel body
+        if ln is None or ln < first_banner:
+            return state['last']
+        name = 'prologue'
         for b, t in banners:
-            if ln is not None and ln >= b:
+            if ln >= b:
                 name = 'L%d %s' % (b, t)
+        state['last'] = name
         return name
     sass = list(csv.reader(run(['ncu', '-i', rep, '--page', 'source', '--csv']).splitlines()))
     # first kernel block whose name matches
@@ -94,7 +101,7 @@ def main():
     T, A, S = sum(tot.values()), sum(alu.values()), max(sum(smp.values()), 1)
     print('\n## region table for %s (%s), SASS instrs matched: %d' % (kern, blk['name'][:60], len(rows)))
     print('   warp-instructions executed: %d total, %d on the ALU pipe; first-instruction executions (warps): %d' % (T, A, grid_warps))
-    for reg in sorted(tot, key=lambda k: (k[0] != 'L', int(re.match(r'L(\d+)', k).group(1)) if k[0] == 'L' else 0)):
+    for reg in sorted(tot, key=lambda k: int(re.match(r'L(\d+)', k).group(1)) if k[0] == 'L' else 0):
         print('   %-72s %5.1f%% instr  %5.1f%% alu  %5.1f%% stall-samples' % (reg, 100 * tot[reg] / T, 100 * alu[reg] / max(A, 1), 100 * smp[reg] / S))
     print('   opcode mix (%% of executed): ' + ', '.join('%s %.1f' % (k, 100 * v / T) for k, v in ops.most_common(16)))
 
