@@ -1,20 +1,23 @@
 #!/usr/bin/env python3
 """bench.py - throughput of the MPEG-2 I/P macroblock path on N B200s (one process per GPU).
 
-Workload (BASELINE.json configs[3], the one the metric is quoted on): 1920x1152, GOP I+15P,
-VECTOR_LEVEL=3, Q_LEVEL=2 (sweep with --q), synthetic S1 "pan" clip built directly in HBM,
---frames per GPU (default 512 = 32 closed GOPs).  Closed GOPs shard across ranks with no data-path
-collective ("weak": every rank encodes its own --frames block of one long sequence; value = all
-pixels / max-over-ranks step time).  A step = one pass of the whole hot path over the batch:
-K1 mb_encode x16 launches, K2 vlc count, K3 scans, K4 headers, K2 vlc write -> body bytes in HBM.
+Default workload = BASELINE.json configs[3], the one the metric is quoted on: 1920x1152, GOP I+15P,
+VECTOR_LEVEL=3, Q_LEVEL=2 (sweep with --q), synthetic S1 "pan" clip built directly in HBM, 512 frames
+(32 closed GOPs) per GPU.  Closed GOPs shard across ranks with no data-path collective; scaling is
+"weak" (every rank encodes its own 512-frame block of one long sequence; value = all pixels /
+max-over-ranks device time).  --config 2|3|5 select the other BASELINE.json configurations
+(5 = 2048x2048 x 1000 frames, a fixed job split by GOP across the ranks: "strong").
 
-  value   : Mpixel/s, inputs already resident in HBM, device time from the library's CUDA events
-            (first launch -> last kernel end, max over ranks)
+A step = one pass of the whole hot path over the batch: K1 mb_encode (one launch per frame index in
+the GOP), K2 vlc count, K3 scans, K4 headers, K2 vlc write -> body bytes in HBM.
+
+  value   : Mpixel/s, inputs already resident in HBM, device time from the library's CUDA events on its
+            launching stream (first launch -> last kernel end), max over ranks
   e2e     : same metric through the streaming C-ABI with HOST buffers (m2v_begin / m2v_push_frames /
             m2v_stop / m2v_drain): pinned host frames -> H2D -> kernels -> D2H of the stream
   roofline: K1 (dominant kernel) algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the CPU oracle (a port: the reference is Verilog and no simulator
-            exists in the image) on the box's host cores over a bounded sample of the same workload.
+            exists in the image or on the GPU box) on the host cores over a bounded sample of the workload.
 """
 import argparse
 import json
@@ -27,13 +30,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, P, VL = 1920, 1152, 15, 3
-# algorithmic HBM bytes per pixel of K1: reads 3.0 (4:4:4 in) + 1.5 (previous recon, P only);
-# writes 1.5 (recon of every frame that is followed by a P-frame).  Averaged over a GOP of P+1 frames.
+CONFIGS = {   # BASELINE.json configs[1..4]  (W, H, pframes_count, VECTOR_LEVEL, default frames per GPU, scaling)
+    2: dict(W=640, H=480, P=0, VL=3, frames=1024, scaling='weak', name='config2: 640x480 I-only'),
+    3: dict(W=1280, H=720, P=7, VL=3, frames=512, scaling='weak', name='config3: 1280x720 I+7P'),
+    4: dict(W=1920, H=1152, P=15, VL=3, frames=512, scaling='weak', name='config4: 1920x1152 I+15P'),
+    5: dict(W=2048, H=2048, P=15, VL=3, frames=1000, scaling='strong', name='config5: 2048x2048 I+15P, 1000 frames total'),
+}
+
+
 def alg_bytes_per_pixel(p):
-    reads = (3.0 + p * 4.5) / (p + 1)
-    writes = 1.5 * p / (p + 1)
-    return reads, writes
+    """algorithmic HBM bytes per pixel of K1: reads 3.0 (4:4:4 in) + 1.5 (previous recon,
+    P-frames only); writes 1.5 (recon of every frame that is followed by a P-frame); GOP average."""
+    return (3.0 + p * 4.5) / (p + 1), 1.5 * p / (p + 1)
 
 
 class ClockSampler(threading.Thread):
@@ -52,7 +60,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in o])
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(0.05)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
@@ -66,67 +74,73 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(self.samples)}
 
 
-def cpu_oracle_throughput(nthreads, gops_per_thread, q, steps=1):
-    """GOP-parallel run of the CPU oracle on host threads (ctypes releases the GIL).  Returns
-    (Mpixel/s, seconds, frames)."""
-    import numpy as np
+def cpu_oracle_throughput(cfg, nthreads, q, steps=1):
+    """GOP-parallel run of the CPU oracle on host threads (ctypes releases the GIL): one GOP of the
+    workload per thread per step.  Returns (Mpixel/s, seconds of the best step, frames per step)."""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import oracle_binding as ob
     import __graft_entry__ as ge
     synth = ge.load_synth()
-    gop = P + 1
-    clip = synth.s1_pan(20260929, gop, W, H)                    # one GOP of the workload, reused by every thread
+    W, H, P, VL = cfg['W'], cfg['H'], cfg['P'], cfg['VL']
+    gop = max(P + 1, 4 if P == 0 else 1)                        # I-only: 4 frames per thread
+    clip = synth.s1_pan(20260929, gop, W, H)
     ob.lib()
     best = None
     for _ in range(steps):
         def work(i):
-            for g in range(gops_per_thread):
-                ob.encode_range(clip, (i * gops_per_thread + g) * gop, W // 16, H // 16, P, VL=VL, Q=q)
+            ob.encode_range(clip, i * gop * (P + 1), W // 16, H // 16, P, VL=VL, Q=q)
         th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         t0 = time.perf_counter()
         for t in th: t.start()
         for t in th: t.join()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    frames = nthreads * gops_per_thread * gop
+    frames = nthreads * gop
     return frames * W * H / best / 1e6, best, frames
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--frames', type=int, default=512, help='frames per GPU (whole GOPs of 16)')
+    ap.add_argument('--config', type=int, default=4, choices=sorted(CONFIGS))
+    ap.add_argument('--frames', type=int, default=0, help='frames per GPU (config 5: total frames); 0 = config default')
     ap.add_argument('--q', type=int, default=2, help='Q_LEVEL 1..4')
     ap.add_argument('--e2e-frames', type=int, default=256)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.frames:
+        cfg['frames'] = a.frames
+    W, H, P, VL = cfg['W'], cfg['H'], cfg['P'], cfg['VL']
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     cores = os.cpu_count() or 1
-    config = {'workload': 'config4: 1920x1152 I+15P VECTOR_LEVEL=3 Q_LEVEL=%d, %d frames/GPU synthetic S1 pan' % (a.q, a.frames),
-              'frames_per_gpu': a.frames, 'gop': P + 1, 'sharding': 'closed GOPs, contiguous blocks per rank',
-              'l2': 'inputs (%.1f GB/GPU) larger than L2' % (a.frames * 3 * W * H / 1e9)}
+    gop = P + 1
+    config = {'workload': '%s VECTOR_LEVEL=%d Q_LEVEL=%d, %d frames%s, synthetic S1 pan' %
+                          (cfg['name'], VL, a.q, cfg['frames'], '/GPU' if cfg['scaling'] == 'weak' else ' total'),
+              'width': W, 'height': H, 'gop': gop, 'sharding': 'closed GOPs, contiguous blocks per rank, no data-path collective',
+              'l2': 'inputs (%.1f GB per GPU) larger than the 126 MB L2' % (cfg['frames'] * 3 * W * H / 1e9 / (world if cfg['scaling'] == 'strong' else 1))}
 
     if a.impl == 'reference':
-        # the reference's own implementation is Verilog; no simulator in the image -> the CPU oracle
-        # (a port) on all host threads, bounded sample: one GOP per thread per step
+        # The reference's own implementation is a Verilog module; neither this image nor the GPU box has a
+        # simulator, so the timed CPU arm is the oracle port on all host threads, one GOP per thread per step.
         if rank != 0:
             return
         nthr = min(cores, 64)
-        cpu_oracle_throughput(nthr, 1, a.q, steps=max(1, min(a.warmup, 1)))
-        v, dt, fr = cpu_oracle_throughput(nthr, 1, a.q, steps=a.steps)
-        line = {'impl': 'reference', 'metric': 'Mpixel/s', 'value': round(v, 3), 'unit': 'Mpixel/s', 'n_gpus': a.gpus,
-                'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(dt * 1e3, 3), 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': round(v, 3), 'unit': 'Mpixel/s', 'cores': nthr, 'kind': 'port',
-                                 'sample': '%d frames (1 GOP of 16 per thread) of the config-4 clip per step' % fr},
-                'e2e': {'value': round(v, 3), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'fps_1920x1152': round(v * 1e6 / (W * H), 2)}
-        print(json.dumps(line))
+        cpu_oracle_throughput(cfg, nthr, a.q, steps=1)
+        v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=max(1, a.steps))
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'Mpixel/s', 'value': round(v, 3), 'unit': 'Mpixel/s', 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': round(dt * 1e3, 3), 'higher_is_better': True, 'scaling': cfg['scaling'],
+            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': round(v, 3), 'unit': 'Mpixel/s', 'cores': nthr, 'kind': 'port',
+                             'sample': '%d frames (%d per host thread) of the workload clip per step' % (fr, fr // nthr)},
+            'e2e': {'value': round(v, 3), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'fps': round(v * 1e6 / (W * H), 2)}))
         return
 
     import numpy as np
@@ -139,11 +153,17 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    gop = P + 1
-    F = a.frames // gop * gop
-    n0 = rank * F                                              # this rank's block of the long sequence
-    frames = torch.empty((F, 3, H, W), dtype=torch.uint8, device=dev)
-    synth.s1_pan_torch(20260929 + rank, F, W, H, dev, out=frames)
+    if cfg['scaling'] == 'weak':
+        F = max(gop, cfg['frames'] // gop * gop)
+        n0 = rank * F                                          # this rank's block of one long sequence
+        total_frames = world * F
+    else:
+        n0, n1 = sharding.gop_partition(cfg['frames'], P, world)[rank]
+        F = n1 - n0
+        total_frames = cfg['frames']
+    frames = torch.empty((max(F, 1), 3, H, W), dtype=torch.uint8, device=dev)
+    if F:
+        synth.s1_pan_torch(20260929 + rank, F, W, H, dev, out=frames)
     torch.cuda.synchronize()
     enc = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q)
     enc.set_timing(True)
@@ -155,65 +175,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    body_len = 0
+    body_len, ptr = 0, 0
     for _ in range(a.warmup):
-        _, body_len = enc.encode_gops_device(frames.data_ptr(), F, n0, mbw, mbh, P)
+        if F:
+            ptr, body_len = enc.encode_gops_device(frames.data_ptr(), F, n0, mbw, mbh, P)
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = enc.launch_count
     dev_ms = 0.0; kms = [0.0] * 5
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        ptr, body_len = enc.encode_gops_device(frames.data_ptr(), F, n0, mbw, mbh, P)
-        k = enc.kernel_ms()
-        kms = [x + y for x, y in zip(kms, k)]
-        dev_ms += k[4]
+        if F:
+            ptr, body_len = enc.encode_gops_device(frames.data_ptr(), F, n0, mbw, mbh, P)
+            k = enc.kernel_ms()
+            kms = [x + y for x, y in zip(kms, k)]
+            dev_ms += k[4]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True; sampler.join()
     launches = enc.launch_count - l0
-    # device time, max over ranks
-    tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)       # device time, max over ranks
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max = float(tm[0]), float(tm[1])
-    ms_per_step = dev_ms_max / a.steps
-    total_px = world * F * W * H
-    value = total_px / (ms_per_step * 1e-3) / 1e6
+    ms_per_step = float(tm[0]) / a.steps
+    value = total_frames * W * H / (ms_per_step * 1e-3) / 1e6
 
-    # gather the per-rank bodies on rank 0 (NCCL, payload only) - outside the timed region at N>1
+    # gather the per-rank bodies on rank 0 over NCCL (payload only, ~0.02-0.07 B/pixel) and assemble
+    class _DevView:                                            # zero-copy view of the library's device buffer
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '|u1', 'data': (p, False), 'version': 3}
+    gather_ms = 0.0
     if world > 1:
-        class _DevView:                                        # zero-copy view of the library's device buffer
-            def __init__(self, p, n):
-                self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '|u1', 'data': (p, False), 'version': 3}
-        bt = torch.as_tensor(_DevView(ptr, body_len), device=dev).clone()
+        bt = torch.as_tensor(_DevView(ptr, body_len), device=dev).clone() if body_len else torch.empty(0, dtype=torch.uint8, device=dev)
+        barrier(); tg = time.perf_counter()
         bodies = sharding.gather_bodies(bt, dist, dev)
-        total_stream = (34 + sum(int(b.numel()) for b in bodies) + 36) if rank == 0 else 0
+        torch.cuda.synchronize(); gather_ms = (time.perf_counter() - tg) * 1e3
+        total_stream = len(sharding.assemble_stream(pkg.sequence_header(mbw, mbh), bodies, pkg.finish_stream)) if rank == 0 else 0
     else:
-        total_stream = 34 + body_len + 36
+        total_stream = 32 * ((34 + body_len + 4) // 32 + 1)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier(); dist.destroy_process_group()
+        dist.barrier(); dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (K1 = all mb_encode launches of a step) ----
+    # ---- roofline of the dominant kernel (K1 = the mb_encode launches of a step) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    peak = float(peaks.get('hbm_gbs', 6650.0)); peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650'
+    peak = float(peaks.get('hbm_gbs', 6650.0))
     rd, wr = alg_bytes_per_pixel(P)
     k1_ms = kms[0] / a.steps
-    k1_launches = P + 1
+    k1_launches = min(gop, F)
     bytes_per_launch = F * W * H * (rd + wr) / k1_launches
     achieved = bytes_per_launch / (k1_ms / k1_launches * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': 'k1_mb_encode', 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
-                'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
-                'alg_bytes_per_pixel': {'read': round(rd, 4), 'write': round(wr, 4)},
+                'frac': round(achieved / peak, 4), 'traffic': None,
+                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                'alg_bytes_per_pixel': {'read': round(rd, 4), 'write': round(wr, 4)}, 'alg_bytes_per_launch': int(bytes_per_launch),
                 'avg_launch_ms': round(k1_ms / k1_launches, 4), 'launches_per_step': k1_launches,
-                'note': 'K1 on P-frames is integer-ALU bound (full-search SAD), not HBM bound: see DESIGN.md',
+                'note': 'K1 on P-frames is bound by the integer ALU pipe (full-search SAD + transforms), not by HBM; see DESIGN.md section 3 and profiles/',
                 'phase_ms_per_step': {'k1_mb_encode': round(k1_ms, 3), 'k2_vlc_count': round(kms[1] / a.steps, 3),
                                       'k3_scans_k4_headers': round(kms[2] / a.steps, 3), 'k2_vlc_write': round(kms[3] / a.steps, 3)}}
     try:
@@ -224,7 +246,7 @@ def main():
     # ---- end-to-end through the streaming C-ABI with host buffers ----
     e2e = None
     if not a.no_e2e and world == 1:
-        Fe = min(a.e2e_frames // gop * gop, F)
+        Fe = max(gop, min(a.e2e_frames // gop * gop, F))
         host = torch.empty((Fe, 3, H, W), dtype=torch.uint8).pin_memory()
         host.copy_(frames[:Fe])
         hnp = host.numpy()
@@ -234,7 +256,7 @@ def main():
             data, last = e2.drain(cap=64 << 20)
             assert last
             return len(data)
-        for _ in range(max(1, min(a.warmup, 2))):
+        for _ in range(2):
             nbytes = one()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -244,23 +266,24 @@ def main():
         dt = (time.perf_counter() - t1) / a.steps
         e2e = {'value': round(Fe * W * H / dt / 1e6, 2), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': Fe * 3 * W * H,
                'd2h_bytes_per_step': nbytes, 'frames': Fe, 'ms_per_step': round(dt * 1e3, 3),
-               'api': 'm2v_begin/m2v_push_frames(pinned host)/m2v_stop/m2v_drain'}
+               'api': 'm2v_begin / m2v_push_frames(pinned host) / m2v_stop / m2v_drain',
+               'note': 'H2D of 3 B/pixel dominates; PCIe ceiling on this box is ~54 GB/s = ~18 Gpixel/s (profiles/r01_h2d_probe.txt)'}
         e2.close()
 
     cpu = None
     if not a.no_cpu and world == 1:
         nthr = min(cores, 64)
-        v, dt, fr = cpu_oracle_throughput(nthr, 1, a.q, steps=1)
+        v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=1)
         cpu = {'value': round(v, 3), 'unit': 'Mpixel/s', 'cores': nthr, 'kind': 'port',
-               'sample': '%d frames (1 GOP of 16 per host thread) of the config-4 clip, %.1f s' % (fr, dt)}
+               'sample': '%d frames (%d per host thread, GOP-parallel) of the workload clip, %.1f s' % (fr, fr // nthr, dt)}
 
     line = {'metric': 'Mpixel/s', 'value': round(value, 2), 'unit': 'Mpixel/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-            'ms_per_step': round(ms_per_step, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u8', 'data': 'synthetic', 'config': config, 'fps_1920x1152': round(value * 1e6 / (W * H), 1),
-            'wall_ms_per_step': round(wall_ms_max / a.steps, 3), 'stream_bytes': total_stream,
-            'bytes_per_pixel_out': round(body_len / (F * W * H), 5),
+            'ms_per_step': round(ms_per_step, 3), 'higher_is_better': True, 'scaling': cfg['scaling'], 'vs_baseline': None,
+            'dtype': 'u8', 'data': 'synthetic', 'config': config, 'fps': round(value * 1e6 / (W * H), 1),
+            'wall_ms_per_step': round(float(tm[1]) / a.steps, 3), 'stream_bytes': total_stream, 'gather_ms': round(gather_ms, 3),
+            'bytes_per_pixel_out': round(body_len / max(F * W * H, 1), 5),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': sampler.summary(),
-            'published_yardstick': {'fpga_mpixel_s': 268, 'fpga_fps_1920x1152': 121, 'source': 'reference README.md:22 (Kintex-7, not comparable hardware)'}}
+            'published_yardstick': {'fpga_mpixel_s': 268, 'fpga_fps_1920x1152': 121, 'source': 'reference README.md:22 (Kintex-7 FPGA; context only)'}}
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -53,9 +53,11 @@ def main():
             m = re.match(r'\s*\.text\.(\S+):', l)
             if m:
                 cur = m.group(1); continue
-            m = re.search(r'//## File ".*?", line (\d+)', l)
+            m = re.search(r'//## File "(.*?)", line (\d+)', l)
             if m:
-                line = int(m.group(1)); continue
+                # lines of other files (CUDA intrinsic headers) are treated like inlined helpers
+                line = int(m.group(2)) if m.group(1).endswith('m2v_kernels.cu') else None
+                continue
             if cur and kern in cur:
                 m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
                 if m:
