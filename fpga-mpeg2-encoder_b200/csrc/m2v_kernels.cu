@@ -205,40 +205,52 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     const int W = p.W, CWp = p.CWp;
     const size_t ysz = (size_t)W * p.H;
 
-    // one elected lane arms the stage's mbarrier with the byte count and issues the TMA boxes
-    auto issue = [&](unsigned idx, int stg) {
+    // macroblock index -> (GOP, block row, block column): decoded once per macroblock (all lanes), reused
+    // by the TMA issue of the prefetch and by the encode one iteration later
+    struct MbPos { int g, by, bx; };
+    auto decode = [&](unsigned idx) {
+        MbPos m;
         const unsigned g = idx / (unsigned)p.nmb, mb = idx - g * p.nmb;
-        const int by = (int)(mb / (unsigned)p.mbw), bx = (int)mb - by * p.mbw;
-        const int n = (int)g * (p.P + 1) + p.t;
+        m.g = (int)g; m.by = (int)(mb / (unsigned)p.mbw); m.bx = (int)mb - m.by * p.mbw;
+        return m;
+    };
+    // one elected lane arms the stage's mbarrier with the byte count and issues the TMA boxes
+    auto issue = [&](const MbPos &m, int stg) {
+        const int n = m.g * (p.P + 1) + p.t;
         StageSmem &S = s.st[stg];
         const uint32_t bar = smem_u32(&s.bar[stg]);
         mbar_expect_tx(bar, TX_BYTES);
-        tma_load_4d(smem_u32(S.curY), &tm_in, bx * 16, by * 16, 0, n, bar);
-        tma_load_4d(smem_u32(S.curU), &tm_in, bx * 16, by * 16, 1, n, bar);
-        tma_load_4d(smem_u32(S.curV), &tm_in, bx * 16, by * 16, 2, n, bar);
+        tma_load_4d(smem_u32(S.curY), &tm_in, m.bx * 16, m.by * 16, 0, n, bar);
+        tma_load_4d(smem_u32(S.curU), &tm_in, m.bx * 16, m.by * 16, 1, n, bar);
+        tma_load_4d(smem_u32(S.curV), &tm_in, m.bx * 16, m.by * 16, 2, n, bar);
         if (PFRAME) {
             // out-of-frame parts of a box are zero-filled by TMA; they only ever feed candidates the border
             // rule disables (RTL:1642-1645, 1757-1760).  (RTL:1350-1425, 1613-1629 fetch the same windows.)
-            const int cx0 = (bx * 8 - 8) & ~15;
-            tma_load_3d(smem_u32(S.winY), &tm_refY, bx * 16 - 16, by * 16 - (R + 1), (int)g, bar);
-            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, by * 8 - 4, 0, (int)g, bar);
-            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, cx0, by * 8 - 4, 1, (int)g, bar);
+            const int cx0 = (m.bx * 8 - 8) & ~15;
+            tma_load_3d(smem_u32(S.winY), &tm_refY, m.bx * 16 - 16, m.by * 16 - (R + 1), m.g, bar);
+            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);
+            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, cx0, m.by * 8 - 4, 1, m.g, bar);
         }
     };
+    MbPos cur = decode(gwarp);
     if (lane == 0) {
         mbar_init(smem_u32(&s.bar[0]), 1); mbar_init(smem_u32(&s.bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        issue(gwarp, 0);
+        issue(cur, 0);
     }
     __syncwarp();
     uint32_t phase = 0;
     int stg = 0;
+    MbPos nxt = cur;
 #pragma unroll 1
-    for (unsigned idx = gwarp; idx < p.total; idx += nwarps, stg ^= 1) {
-    if (lane == 0 && idx + nwarps < p.total) { fence_proxy_async(); issue(idx + nwarps, stg ^ 1); }
-    const unsigned g = idx / (unsigned)p.nmb, mb = idx - g * p.nmb;
-    const int by = (int)(mb / (unsigned)p.mbw), bx = (int)mb - by * p.mbw;
+    for (unsigned idx = gwarp; idx < p.total; idx += nwarps, stg ^= 1, cur = nxt) {
+    if (idx + nwarps < p.total) {
+        nxt = decode(idx + nwarps);
+        if (lane == 0) { fence_proxy_async(); issue(nxt, stg ^ 1); }
+    }
+    const int g = cur.g, by = cur.by, bx = cur.bx;
+    const unsigned mb = (unsigned)(by * p.mbw + bx);
     const long n = (long)g * (p.P + 1) + p.t;               // frame index inside the batch
     const int Y0 = by * 16, X0 = bx * 16;
     StageSmem &S = s.st[stg];
@@ -287,18 +299,21 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                     }
                 }
             }
+            // key = SAD<<10 | (R-dy)<<5 | (R-dx): minimum = smallest SAD, ties -> largest dy, then largest dx
+            // (RTL:1696-1710).  SAD >= 4096 disqualifies (RTL:1669-1670)  <=>  key >= 1<<22, checked once at
+            // the end.  The border rule (RTL:1642-1645) is warp-uniform in dy and per-lane in dx.
             uint32_t best = 0xFFFFFFFFu;
             const int dx = (lane & 15) - R;
+            const int dylo = (by == 0) ? R : 0, dyhi = (by == p.mbh - 1) ? R : 2 * R;
 #pragma unroll
             for (int dyi = 0; dyi <= 2 * R; dyi++) {
-                uint32_t tot = acc[dyi] + __shfl_xor_sync(FULL, acc[dyi], 16);
-                const int dy = dyi - R;
-                bool dis = (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0) || (by == 0 && dy < 0) || (by == p.mbh - 1 && dy > 0);
-                // SAD >= 4096 disqualifies (RTL:1669-1670); ties: largest dy, then largest dx (RTL:1696-1710)
-                if (lane <= 2 * R && !dis && tot < 4096u) best = min(best, (tot << 10) | ((uint32_t)(R - dy) << 5) | (uint32_t)(R - dx));
+                if (dyi < dylo || dyi > dyhi) continue;
+                const uint32_t tot = acc[dyi] + __shfl_xor_sync(FULL, acc[dyi], 16);
+                best = min(best, tot * 1024u + (uint32_t)(((2 * R - dyi) << 5) + R - dx));
             }
+            if (lane > 2 * R || (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0)) best = 0xFFFFFFFFu;
             best = __reduce_min_sync(FULL, best);
-            if (best != 0xFFFFFFFFu) { fmvy = R - (int)((best >> 5) & 31); fmvx = R - (int)(best & 31); }
+            if (best < (1u << 22)) { fmvy = R - (int)((best >> 5) & 31); fmvx = R - (int)(best & 31); }
         }
 
         // ---- half-pel refinement + intra/inter decision (RTL:1743-1816).  lane = 2*y + half. ----
@@ -487,7 +502,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         if (round == 0) { for (int k = 0; k < 4; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (32 >> k) : 0; }
         else { for (int k = 0; k < 2; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (2 >> k) : 0; }
         __syncwarp();
-        if (act) {                                               // inverse rows (in place)
+        // A tile whose levels are all zero reconstructs to exactly the prediction (all-zero input gives
+        // (128)>>8 = 0 after the row pass and (8192)>>14 = 0 after the column pass), so its inverse
+        // transform is skipped; the decision is per 8-lane group.
+        const bool inv = act && ((nzm >> (8 * (lane >> 3))) & 0xFF);
+        if (inv) {                                               // inverse rows (in place)
 #pragma unroll
             for (int j = 0; j < 8; j++) x[j] = tt[v * 8 + j];
             idct_row(x, o);
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
         }
         __syncwarp();
-        if (act) {                                               // inverse columns, add prediction, clip (RTL:2352)
+        if (inv) {                                               // inverse columns, add prediction, clip (RTL:2352)
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
             idct_col(x, o);
@@ -639,105 +658,130 @@ struct K2Args {
     int mbw, mbh, nmb, P; long n0; long total;
 };
 
-template <bool WRITE>
-__global__ void __launch_bounds__(256) k2_vlc(K2Args p) {
-    const int lane = threadIdx.x & 31;
-    const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (gw >= p.total) return;
-    const long f = gw / p.nmb;
-    const int mb = (int)(gw % p.nmb), by = mb / p.mbw, bx = mb % p.mbw;
-    const int k = (int)((p.n0 + f) % (p.P + 1));
-    const uint32_t info = p.mbinfo[gw];
+// K2: ONE THREAD PER MACROBLOCK, lanes of a warp = consecutive macroblocks (RTL:2718-2847).
+// The levels are sparse (typically a handful of non-zero values in the 384 of a macroblock), so the
+// work is latency/issue bound, not data bound: a thread reads its record, skips tiles whose cbp bit is
+// clear, and for a coded tile walks 16-level chunks by find-first-set over a non-zero mask.  A warp thus
+// retires 32 macroblocks in about the time the busiest of them needs.  Codes are accumulated MSB-first in
+// a 64-bit window and ORed into the zero-initialised stream one 32-bit word at a time (RED.OR).
+struct BitAcc {                       // MSB-first accumulator aligned to 32-bit stream words
+    uint32_t *w; unsigned long long acc; int n;
+    __device__ __forceinline__ void start(uint32_t *words, unsigned long long bitpos) {
+        w = words + (bitpos >> 5); n = (int)(bitpos & 31); acc = 0;      // leading zero bits are harmless: we OR
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        acc = (acc << len) | code; n += len;
+        if (n >= 32) {
+            atomicOr(w++, __byte_perm((uint32_t)(acc >> (n - 32)), 0, 0x0123));
+            n -= 32; acc &= (1ull << n) - 1;
+        }
+    }
+    __device__ __forceinline__ void flush() { if (n) atomicOr(w, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123)); }
+};
+struct BitCount {
+    int n;
+    __device__ __forceinline__ void put(uint32_t, int len) { n += len; }
+};
+
+template <typename Emit>
+__device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__ zz, int k, uint32_t info, uint32_t li, bool has_left) {
     const int inter = info & 1, mvx = (int8_t)(info >> 8), mvy = (int8_t)(info >> 16), cbp = (info >> 24) & 63;
-    const int16_t *zz = p.coefs + (size_t)gw * 384;
     // predictors from the left neighbour; reset at slice start (RTL:2713-2715), DC reset by an inter
     // macroblock (RTL:2786-2792), PMV reset by an intra macroblock (RTL:2771-2773)
     int pmvx = 0, pmvy = 0, dcp[3] = {0, 0, 0};
-    if (bx > 0) {
-        const uint32_t li = p.mbinfo[gw - 1];
+    if (has_left) {
         if (li & 1) { pmvx = (int8_t)(li >> 8); pmvy = (int8_t)(li >> 16); }
-        else { dcp[0] = zz[-384 + 3 * 64]; dcp[1] = zz[-384 + 4 * 64]; dcp[2] = zz[-384 + 5 * 64]; }
+        else if (!inter) { dcp[0] = zz[-384 + 3 * 64]; dcp[1] = zz[-384 + 4 * 64]; dcp[2] = zz[-384 + 5 * 64]; }
     }
-    unsigned long long pos = 0;
-    if (WRITE) {
-        const int hdr = (k == 0) ? 25 : 18;
-        pos = 8ull * (p.frame_off[f] + hdr + p.slice_off[f * p.mbh + by]) + p.mb_off[gw];
-    }
-    uint32_t bits = 0;
     // ---- macroblock header (RTL:2722-2767) ----
-    {
-        uint32_t c; int l;
-        if (!inter && k != 0) { c = 0x23; l = 6; } else if (inter && cbp == 0) { c = 0x09; l = 4; } else { c = 0x03; l = 2; }
-        if (WRITE && lane == 0) put_bits(p.out, pos, c, l);
-        bits += l;
-        if (inter) {
+    if (!inter && k != 0) out.put(0x23u, 6); else if (inter && cbp == 0) out.put(0x09u, 4); else out.put(0x03u, 2);
+    if (inter) {
 #pragma unroll
-            for (int comp = 0; comp < 2; comp++) {
-                int d = comp ? mvy - pmvy : mvx - pmvx;
-                if (d > 15) d -= 32; else if (d < -16) d += 32;
-                const uint32_t e = c_vlc_motion[abs(d)];
-                c = e & 0xFFFF; l = (int)(e >> 16);
-                if (d != 0) { c = (c << 1) | (d < 0); l++; }
-                if (WRITE && lane == 0) put_bits(p.out, pos + bits, c, l);
-                bits += l;
-            }
-            const uint32_t e = c_vlc_cbp[cbp];
-            if (WRITE && lane == 0) put_bits(p.out, pos + bits, e & 0xFFFF, (int)(e >> 16));
-            bits += e >> 16;
+        for (int comp = 0; comp < 2; comp++) {
+            int d = comp ? mvy - pmvy : mvx - pmvx;
+            if (d > 15) d -= 32; else if (d < -16) d += 32;
+            const uint32_t e = c_vlc_motion[abs(d)];
+            uint32_t c = e & 0xFFFF; int l = (int)(e >> 16);
+            if (d != 0) { c = (c << 1) | (d < 0); l++; }
+            out.put(c, l);
         }
+        const uint32_t e = c_vlc_cbp[cbp];
+        out.put(e & 0xFFFF, (int)(e >> 16));
     }
-    // ---- tiles (RTL:2777-2847).  lane L owns scan positions L and L+32. ----
+    // ---- tiles (RTL:2777-2847) ----
     int prev_dc = 0;
-    int lv0[6], lv1[6];
-#pragma unroll
-    for (int t = 0; t < 6; t++) { lv0[t] = zz[t * 64 + lane]; lv1[t] = zz[t * 64 + 32 + lane]; }
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < 6; t++) {
-        const int v0 = lv0[t], v1 = lv1[t];
-        const int dc = __shfl_sync(FULL, v0, 0);
-        const int comp = t < 4 ? 0 : t - 3;
-        const int pred = (t >= 1 && t <= 3) ? prev_dc : dcp[comp];
-        prev_dc = dc;
-        if (!((cbp >> (5 - t)) & 1)) continue;                     // inter tile with no level: nothing (RTL:2799,2804,2828)
-        unsigned long long m = (unsigned long long)__ballot_sync(FULL, v0 != 0) | ((unsigned long long)__ballot_sync(FULL, v1 != 0) << 32);
-        if (!inter) m |= 1ull;                                     // the DC slot always "precedes" the first AC run
-        uint32_t cA = 0, cB = 0; int lA = 0, lB = 0;
-        if (lane == 0) {
-            if (inter) {                                           // RTL:2795-2806
-                if (v0 == 1 || v0 == -1) { cA = 2u | (v0 < 0); lA = 2; }
-                else if (v0 != 0) ac_code(v0, 0, cA, lA);
-            } else {                                               // RTL:2808-2821
-                const int diff = dc - pred, a = abs(diff);
-                const int size = 32 - __clz(a);
-                const uint32_t e = t < 4 ? c_vlc_dcy[size] : c_vlc_dcc[size];
-                const uint32_t db = (uint32_t)(diff < 0 ? diff + (1 << size) - 1 : diff) & ((1u << size) - 1);
-                cA = ((e & 0xFFFF) << size) | db; lA = (int)(e >> 16) + size;
+        if (!((cbp >> (5 - t)) & 1)) continue;                    // inter tile without a level: nothing (RTL:2799,2804,2828)
+        const uint4 *src = (const uint4 *)(zz + t * 64);
+        int prevpos = inter ? -1 : 0;                             // the intra DC slot anchors the first run (RTL:2824)
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ch++) {
+            const uint4 a = __ldg(src + 2 * ch), b = __ldg(src + 2 * ch + 1);
+            const uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+            uint32_t m = 0;
+            m |= ((w0 & 0xFFFFu) ? 1u : 0u) | ((w0 >> 16) ? 2u : 0u);
+            m |= ((w1 & 0xFFFFu) ? 4u : 0u) | ((w1 >> 16) ? 8u : 0u);
+            m |= ((w2 & 0xFFFFu) ? 16u : 0u) | ((w2 >> 16) ? 32u : 0u);
+            m |= ((w3 & 0xFFFFu) ? 64u : 0u) | ((w3 >> 16) ? 128u : 0u);
+            m |= ((w4 & 0xFFFFu) ? 256u : 0u) | ((w4 >> 16) ? 512u : 0u);
+            m |= ((w5 & 0xFFFFu) ? 1024u : 0u) | ((w5 >> 16) ? 2048u : 0u);
+            m |= ((w6 & 0xFFFFu) ? 4096u : 0u) | ((w6 >> 16) ? 8192u : 0u);
+            m |= ((w7 & 0xFFFFu) ? 16384u : 0u) | ((w7 >> 16) ? 32768u : 0u);
+            if (ch == 0) {
+                const int dc = (int16_t)(w0 & 0xFFFF);
+                if (!inter) {                                     // intra DC (RTL:2808-2821)
+                    const int pred = (t >= 1 && t <= 3) ? prev_dc : dcp[t < 4 ? 0 : t - 3];
+                    const int diff = dc - pred, ad = abs(diff), size = 32 - __clz(ad);
+                    const uint32_t e = t < 4 ? c_vlc_dcy[size] : c_vlc_dcc[size];
+                    const uint32_t db = (uint32_t)(diff < 0 ? diff + (1 << size) - 1 : diff) & ((1u << size) - 1);
+                    out.put(((e & 0xFFFF) << size) | db, (int)(e >> 16) + size);
+                    m &= ~1u;
+                    prev_dc = dc;
+                } else if (dc == 1 || dc == -1) {                 // first coefficient +-1 of an inter tile: '1s' (RTL:2798-2802)
+                    out.put(2u | (dc < 0), 2);
+                    m &= ~1u; prevpos = 0;
+                }
             }
-        } else if (v0 != 0) {
-            const unsigned long long below = m & ((1ull << lane) - 1);
-            const int prev = below ? 63 - __clzll(below) : -1;
-            ac_code(v0, lane - prev - 1, cA, lA);
+            while (m) {
+                const int b2 = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t lo = (b2 & 4) ? ((b2 & 2) ? w3 : w2) : ((b2 & 2) ? w1 : w0);
+                const uint32_t hi = (b2 & 4) ? ((b2 & 2) ? w7 : w6) : ((b2 & 2) ? w5 : w4);
+                const uint32_t ws = (b2 & 8) ? hi : lo;
+                const int v = (b2 & 1) ? ((int32_t)ws >> 16) : (int)(int16_t)(ws & 0xFFFF);
+                const int pos = 16 * ch + b2;
+                uint32_t c; int l;
+                ac_code(v, pos - prevpos - 1, c, l);              // RTL:2825-2833
+                prevpos = pos;
+                out.put(c, l);
+            }
         }
-        if (v1 != 0) {
-            const unsigned long long below = m & ((1ull << (lane + 32)) - 1);
-            const int prev = below ? 63 - __clzll(below) : -1;
-            ac_code(v1, lane + 32 - prev - 1, cB, lB);
-        }
-        // inclusive warp scan of both length streams at once (packed 16+16)
-        uint32_t sc = (uint32_t)lA | ((uint32_t)lB << 16);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t nb = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += nb; }
-        const uint32_t tot = __shfl_sync(FULL, sc, 31);
-        const uint32_t totA = tot & 0xFFFF, totB = tot >> 16;
-        if (WRITE) {
-            const unsigned long long base = pos + bits;
-            put_bits(p.out, base + ((sc & 0xFFFF) - lA), cA, lA);
-            put_bits(p.out, base + totA + ((sc >> 16) - lB), cB, lB);
-            if (lane == 0) put_bits(p.out, base + totA + totB, 2, 2);      // end of block (RTL:2835,2897-2900)
-        }
-        bits += totA + totB + 2;
+        out.put(2u, 2);                                           // end of block (RTL:2835, 2897-2900)
     }
-    if (!WRITE && lane == 0) p.mb_bits[gw] = bits;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k2_vlc(K2Args p) {
+    const long gw = (long)blockIdx.x * 128 + threadIdx.x;
+    if (gw >= p.total) return;
+    const long f = gw / p.nmb;
+    const int mb = (int)(gw - f * p.nmb), by = mb / p.mbw, bx = mb - by * p.mbw;
+    const int k = (int)((p.n0 + f) % (p.P + 1));
+    const uint32_t info = __ldg(&p.mbinfo[gw]);
+    const uint32_t li = bx > 0 ? __ldg(&p.mbinfo[gw - 1]) : 0u;
+    const int16_t *zz = p.coefs + (size_t)gw * 384;
+    if (!WRITE) {
+        BitCount bc; bc.n = 0;
+        mb_syntax(bc, zz, k, info, li, bx > 0);
+        p.mb_bits[gw] = (uint32_t)bc.n;
+    } else {
+        const int hdr = (k == 0) ? 25 : 18;
+        const unsigned long long pos = 8ull * (__ldg(&p.frame_off[f]) + hdr + __ldg(&p.slice_off[f * p.mbh + by])) + __ldg(&p.mb_off[gw]);
+        BitAcc bw; bw.start(p.out, pos);
+        mb_syntax(bw, zz, k, info, li, bx > 0);
+        bw.flush();
+    }
 }
 
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
@@ -745,8 +789,8 @@ void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
     a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
     a.frame_off = b.frame_off; a.out = b.out_words;
     a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
-    const unsigned grid = (unsigned)((a.total + 7) / 8);
-    if (write) k2_vlc<true><<<grid, 256, 0, st>>>(a); else k2_vlc<false><<<grid, 256, 0, st>>>(a);
+    const unsigned grid = (unsigned)((a.total + 127) / 128);
+    if (write) k2_vlc<true><<<grid, 128, 0, st>>>(a); else k2_vlc<false><<<grid, 128, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
