@@ -152,8 +152,7 @@ struct __align__(128) WarpSmem {
     uint32_t curC[2][8][2];          // current 4:2:0 chroma blocks
     int16_t res[6][64];              // residual, later the zig-zag levels
     uint8_t pred[6][64];             // prediction, later the reconstruction
-    unsigned long long bar[2];       // one mbarrier per stage
-};
+};                                   // 7936 bytes; the two mbarriers of each warp live after the warps' areas
 // the transform scratch (4 tile slots x TSTR words) aliases winC+winY of the stage being encoded:
 // the windows are dead once the prediction has been formed.
 static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratch must fit in the window area");
@@ -195,7 +194,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     constexpr int WROWS = 18 + 2 * R;
     constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 512 + 48 * WROWS : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];     // keeps the .shared address space: LDS/STS, not generic LD/ST
-    __shared__ QEntry qt[64];
+    QEntry *const qt = reinterpret_cast<QEntry *>(smem_raw + sizeof(WarpSmem) * K1_WARPS);   // 64 entries after the warps' areas
+    unsigned long long *const bars = reinterpret_cast<unsigned long long *>(qt + 64) + 2 * (threadIdx.x >> 5);   // one mbarrier per stage
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) qt[threadIdx.x] = d_qtab[p.Q - 1][threadIdx.x];
     __syncthreads();
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     auto issue = [&](const MbPos &m, int stg) {
         const int n = m.g * (p.P + 1) + p.t;
         StageSmem &S = s.st[stg];
-        const uint32_t bar = smem_u32(&s.bar[stg]);
+        const uint32_t bar = smem_u32(&bars[stg]);
         mbar_expect_tx(bar, TX_BYTES);
         tma_load_4d(smem_u32(S.curY), &tm_in, m.bx * 16, m.by * 16, 0, n, bar);
         tma_load_4d(smem_u32(S.curU), &tm_in, m.bx * 16, m.by * 16, 1, n, bar);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     };
     MbPos cur = decode(gwarp);
     if (lane == 0) {
-        mbar_init(smem_u32(&s.bar[0]), 1); mbar_init(smem_u32(&s.bar[1]), 1);
+        mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
         issue(cur, 0);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     const int Y0 = by * 16, X0 = bx * 16;
     StageSmem &S = s.st[stg];
     int32_t *const tmp = reinterpret_cast<int32_t *>(&S.winC[0][0][0]);
-    mbar_wait(smem_u32(&s.bar[stg]), (phase >> stg) & 1u);
+    mbar_wait(smem_u32(&bars[stg]), (phase >> stg) & 1u);
     phase ^= 1u << stg;
 
     // ---- current block: Y as is; U,V 4:4:4 -> 4:2:0 = mean2 of pixel pairs, then mean2 of the two
@@ -452,24 +452,42 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
         }
         __syncwarp();
-        bool nzl = false;
-        if (act) {                                               // columns: B = DCTM * A, round, quantise
+        bool nzl = false, maybe = true;
+        if (act) {                                               // columns: B = DCTM * A (RTL:2054-2057)
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
             fdct8(x, o);
+            if (inter) {
+                // Inter levels are (|C|+2)>>(4+Q) with C = (B+2048)>>12: zero whenever |B| < 4096*(2^(4+Q)-2) - 2048.
+                // Most columns of a well-predicted tile are entirely below that, so the zig-zag tile is
+                // zero-filled with one vector store per lane and only columns that may hold a level are
+                // quantised coefficient by coefficient.
+                const int thr = 4096 * ((1 << (4 + Q)) - 2) - 2048;
+                const int mx = max(max(max(o[0], o[1]), max(o[2], o[3])), max(max(o[4], o[5]), max(o[6], o[7])));
+                const int mn = min(min(min(o[0], o[1]), min(o[2], o[3])), min(min(o[4], o[5]), min(o[6], o[7])));
+                maybe = (mx >= thr) || (mn <= -thr);
+                *(uint4 *)&s.res[tile][v * 8] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        __syncwarp();                                            // zero fill complete before any level is scattered
+        if (act) {                                               // round, quantise, scan, dequantise
             const int b00 = o[0];
             // |C| <= 255*512*512/4096 = 16320, so every level is < 2047 and the RTL's clip (RTL:2075) never
             // acts; the branch on `inter` is warp-uniform and hoisted out of the coefficient loop.
             if (inter) {
+                if (maybe) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int C = (o[i] + 2048) >> 12;                               // RTL:2058
-                    const int yq = (abs(C) + 2) >> (4 + Q);                          // RTL:2070
-                    const int q = C < 0 ? -yq : yq;
-                    s.res[tile][qt[i * 8 + v].zz] = (int16_t)q;                      // zig-zag (RTL:2464)
-                    nzl |= (yq != 0);
-                    const int m = min(yq ? ((2 * yq + 1) << Q) : 0, 2047);           // RTL:2134-2137
-                    o[i] = C < 0 ? -m : m;
+                    for (int i = 0; i < 8; i++) {
+                        const int C = (o[i] + 2048) >> 12;                           // RTL:2058
+                        const int yq = (abs(C) + 2) >> (4 + Q);                      // RTL:2070
+                        const int sgn = (C >> 31) | 1;
+                        if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
+                        const int m = min(yq ? ((2 * yq + 1) << Q) : 0, 2047);       // RTL:2134-2137
+                        o[i] = m * sgn;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) o[i] = 0;
                 }
             } else {
 #pragma unroll
@@ -477,7 +495,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                     const QEntry qe = qt[i * 8 + v];
                     const int C = (o[i] + 2048) >> 12;
                     const int yq = (int)__umulhi((uint32_t)(abs(C) + (int)qe.off) >> Q, qe.recip);   // RTL:2072 (exact division)
-                    const int q = C < 0 ? -yq : yq;
+                    const int q = yq * ((C >> 31) | 1);
                     s.res[tile][qe.zz] = (int16_t)q;
                     int xq = q * (int)qe.W;                                          // RTL:2139-2144, >>> = floor
                     xq = (Q >= 3) ? (xq << (Q - 3)) : (xq >> (3 - Q));
@@ -592,7 +610,7 @@ bool m2v_make_tmaps(M2VBatch &b) {
 static int k1_grid_cap = 0;
 template <int VL, bool PF>
 static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream_t st) {
-    const size_t smem = sizeof(WarpSmem) * K1_WARPS + 128;
+    const size_t smem = sizeof(WarpSmem) * K1_WARPS + 64 * sizeof(QEntry) + 16 * K1_WARPS;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -600,7 +618,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
     }
     if (!k1_grid_cap) {
         int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        k1_grid_cap = sms * 3;                                     // 3 resident CTAs of 8 warps per SM (shared-memory bound)
+        k1_grid_cap = sms * 3;                                     // 3 resident CTAs of 8 warps per SM (shared-memory bound; 4x7 warps at 72 registers measured slower)
     }
     unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
     if (grid > (unsigned)k1_grid_cap) grid = k1_grid_cap;
