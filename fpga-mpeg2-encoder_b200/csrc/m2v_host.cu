@@ -260,10 +260,12 @@ extern "C" int m2v_begin(m2v_encoder *e, int xs, int ys, int P, int *mbw, int *m
     if (mbw) *mbw = e->mbw; if (mbh) *mbh = e->mbh;
     e->frames_encoded = 0; e->staged_frames = 0; e->px_in_frame = 0; e->ended = false;
     e->stage.clear(); e->outq.clear(); e->out_rd = 0;
-    // flush threshold: enough GOPs that one K1 step has >= 32k macroblocks, staging <= 1 GiB
+    // flush threshold: enough GOPs that one K1 step has >= 16k macroblocks (a smaller batch shortens the
+    // un-overlapped first H2D copy and last encode of the pipeline), staging <= 1 GiB
     const long gop = P + 1, nmb = (long)e->mbw * e->mbh;
-    long g = (32768 + nmb - 1) / nmb;
+    long g = (16384 + nmb - 1) / nmb;
     const size_t fsz = (size_t)nmb * 768;
+    while ((size_t)g * gop * fsz < ((size_t)64 << 20)) g++;       // and >= 64 MiB of input, so per-batch overheads stay small
     while (g > 1 && (size_t)g * gop * fsz > ((size_t)1 << 30)) g--;
     e->batch_frames = g * gop;
     // the RTL arms on the first i_en (RTL:1060-1065); the header is emitted then

@@ -3,9 +3,11 @@
 //   K1 mb_encode : one warp per macroblock.  4:4:4->4:2:0 chroma subsample, full-search SAD motion
 //                  estimation, half-pel refinement, intra/inter decision, prediction, 6x 8x8 integer
 //                  DCT, quantise, zig-zag, dequantise, Chen-Wang IDCT, reconstruction.
-//   K2 vlc       : one warp per macroblock.  run/level + VLC; warp scan over per-coefficient code
-//                  lengths; count pass and write pass.
-//   K3 scans     : slice -> frame -> batch prefix sums of bit/byte lengths; K4 writes the headers.
+//   K1 is launched as persistent warps fed by TMA (cp.async.bulk.tensor + mbarrier, double buffered).
+//   K2 vlc       : one thread per macroblock (lanes = consecutive macroblocks of a slice).  run/level +
+//                  VLC over the sparse levels; count pass (bit length per macroblock) and write pass.
+//   K3 scans     : warp inclusive scans over the per-macroblock bit lengths -> offsets in slice, slice
+//                  bytes -> offsets in frame, frame bytes -> offsets in the body; K4 writes the headers.
 //
 // Behaviour follows /root/reference/RTL/mpeg2encoder.v ("RTL") stage by stage; the citations say
 // which lines each block reproduces.  All arithmetic is integer and must be bit-exact.
@@ -642,7 +644,7 @@ void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: entropy layer of one macroblock per warp (RTL:2718-2847)
+// K2: entropy layer, one macroblock per thread (RTL:2718-2847)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void put_bits(uint32_t *words, unsigned long long pos, uint32_t code, int len) {
     if (len <= 0) return;
