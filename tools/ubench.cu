@@ -26,6 +26,9 @@ __global__ void k(uint32_t *out, uint32_t seed) {
             if (OP == 4) { c0 = c0 * a0 + b; c1 = c1 * a1 + b; c2 = c2 * a2 + b; c3 = c3 * a3 + b; }
             if (OP == 5) { c0 += sm[(c0 + a0) & 1023]; c1 += sm[(c1 + a1) & 1023]; c2 += sm[(c2 + a2) & 1023]; c3 += sm[(c3 + a3) & 1023]; }
             if (OP == 6) { c0 = (c0 + a0) ^ b; c1 = (c1 + a1) ^ b; c2 = (c2 + a2) ^ b; c3 = (c3 + a3) ^ b; }
+            if (OP == 8) { c0 = __mulhi((int)c0, 1 << 20) + a0; c1 = __mulhi((int)c1, 1 << 20) + a1; c2 = __mulhi((int)c2, 1 << 20) + a2; c3 = __mulhi((int)c3, 1 << 20) + a3; }
+            if (OP == 9) { c0 = sad4(a0, c1, c0); c1 = c1 * a1 + b; c2 = sad4(a2, c3, c2); c3 = c3 * a3 + b; }
+            if (OP == 10) { c0 = ((int)c0 >> 12) + a0; c1 = ((int)c1 >> 12) + a1; c2 = ((int)c2 >> 12) + a2; c3 = ((int)c3 >> 12) + a3; }
             if (OP == 7) { c0 = __vsub2(c0, a0); c1 = __vsub2(c1, a1); c2 = __vsub2(c2, a2); c3 = __vsub2(c3, a3); }
         }
     }
@@ -55,6 +58,9 @@ int main() {
     run<5>("lds.32 + iadd", 1, d);
     run<6>("iadd+xor (LOP3/IADD3)", 1, d);
     run<7>("vsub2 (emulated)", 1, d);
+    run<8>("mulhi(x,2^20)+a (IMAD.HI)", 1, d);
+    run<9>("half VABSDIFF4 + half IMAD", 1, d);
+    run<10>("(x>>12)+a (SHF+IADD)", 1, d);
     printf("err: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
