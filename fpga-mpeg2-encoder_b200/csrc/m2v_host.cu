@@ -79,7 +79,8 @@ extern "C" int m2v_create(int XL, int YL, int VL, int Q, m2v_encoder **out) {
     if (cudaGetDevice(&e->dev) != cudaSuccess || cudaGetDeviceProperties(&prop, e->dev) != cudaSuccess || prop.major != 10) {
         delete e; return M2V_ENODEV;                          // sm_100a image only; no fallback
     }
-    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess || m2v_upload_tables(Q) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess || m2v_upload_tables(Q) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {           // table uploads ride the legacy stream: finish them before any launch on e->st
         delete e; return M2V_ECUDA;
     }
     for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
@@ -221,7 +222,7 @@ extern "C" int m2v_encode_gops_device(m2v_encoder *e, int mbw, int mbh, int P, c
         if (tot + len > e->d_body.n) {                             // grow, keeping what is there
             DevBuf<uint8_t> nb;
             CK(nb.reserve(std::max((tot + len) * 2, (size_t)1 << 20)));
-            if (tot) CK(cudaMemcpy(nb.p, e->d_body.p, tot, cudaMemcpyDeviceToDevice));
+            if (tot) { CK(cudaMemcpyAsync(nb.p, e->d_body.p, tot, cudaMemcpyDeviceToDevice, e->st)); CK(cudaStreamSynchronize(e->st)); }
             e->d_body.release(); e->d_body = nb;
         }
         CK(cudaMemcpyAsync(e->d_body.p + tot, e->d_out.p, len, cudaMemcpyDeviceToDevice, e->st));
@@ -239,15 +240,17 @@ extern "C" int m2v_encode_gops_host(m2v_encoder *e, int mbw, int mbh, int P, con
     if (rc) return rc;
     if (body_len) *body_len = len;
     if (!h_body || len > cap) { snprintf(e->err, sizeof e->err, "encode_gops_host: need %zu bytes, have %zu", len, cap); return M2V_ESPACE; }
-    CK(cudaMemcpy(h_body, d, len, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(h_body, d, len, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
     return M2V_OK;
 }
 
 extern "C" int m2v_debug_copy(m2v_encoder *e, uint32_t *mbinfo, int16_t *coefs, long count) {
     if (!e || count > e->last_F * e->last_nmb) return M2V_EINVAL;
     CK(cudaSetDevice(e->dev));
-    if (mbinfo) CK(cudaMemcpy(mbinfo, e->d_mbinfo.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
-    if (coefs) CK(cudaMemcpy(coefs, e->d_coefs.p, (size_t)count * 768, cudaMemcpyDeviceToHost));
+    if (mbinfo) CK(cudaMemcpyAsync(mbinfo, e->d_mbinfo.p, (size_t)count * 4, cudaMemcpyDeviceToHost, e->st));
+    if (coefs) CK(cudaMemcpyAsync(coefs, e->d_coefs.p, (size_t)count * 768, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
     return M2V_OK;
 }
 
@@ -285,13 +288,16 @@ static int flush_staged(m2v_encoder *e) {
     CK(cudaSetDevice(e->dev));
     const size_t fsz = (size_t)e->mbw * e->mbh * 768, bytes = fsz * e->staged_frames;
     CK(e->d_in.reserve(bytes));
-    CK(cudaMemcpy(e->d_in.p, e->stage.data(), bytes, cudaMemcpyHostToDevice));
+    // on the encoder's own stream: a non-blocking stream does not synchronise with the legacy default stream,
+    // and a pageable H2D cudaMemcpy may return before its DMA has finished
+    CK(cudaMemcpyAsync(e->d_in.p, e->stage.data(), bytes, cudaMemcpyHostToDevice, e->st));
     const uint8_t *d = nullptr; size_t len = 0;
     int rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, e->d_in.p, e->staged_frames, e->frames_encoded, &d, &len);
     if (rc) return rc;
     const size_t at = e->outq.size();
     e->outq.resize(at + len);
-    CK(cudaMemcpy(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
     e->frames_encoded += e->staged_frames;
     // keep a partially pushed frame at the front of the staging area
     if (e->px_in_frame) memmove(e->stage.data(), e->stage.data() + bytes, fsz);
@@ -324,29 +330,35 @@ extern "C" int m2v_push_frames(m2v_encoder *e, const uint8_t *yuv, long nframes)
     const size_t fsz = (size_t)e->mbw * e->mbh * 768;
     // whole batches go straight from the caller's buffer to HBM (no host staging copy), double
     // buffered: the H2D copy of batch i+1 (copy stream) overlaps the kernels of batch i.
-    if (e->staged_frames == 0 && nframes >= e->batch_frames) {
+    const long gopf = e->P + 1;
+    if (e->staged_frames == 0 && nframes >= gopf) {
         CK(cudaSetDevice(e->dev));
-        const size_t bytes = fsz * e->batch_frames;
+        // every whole GOP goes directly; only a trailing partial GOP is staged on the host
+        const long direct = nframes / gopf * gopf;
+        const long bf = std::min(e->batch_frames, direct);
+        const size_t bytes = fsz * bf;
         CK(e->d_in.reserve(bytes)); CK(e->d_in2.reserve(bytes));
         uint8_t *dbuf[2] = {e->d_in.p, e->d_in2.p};
-        const long nb = nframes / e->batch_frames;
-        CK(cudaMemcpyAsync(dbuf[0], yuv, bytes, cudaMemcpyHostToDevice, e->st_copy));
+        const long nb = (direct + bf - 1) / bf;
+        auto cnt = [&](long i) { return std::min(bf, direct - i * bf); };
+        CK(cudaMemcpyAsync(dbuf[0], yuv, fsz * cnt(0), cudaMemcpyHostToDevice, e->st_copy));
         CK(cudaEventRecord(e->ev_copy[0], e->st_copy));
         for (long i = 0; i < nb; i++) {
             if (i + 1 < nb) {
-                CK(cudaMemcpyAsync(dbuf[(i + 1) & 1], yuv + (size_t)(i + 1) * bytes, bytes, cudaMemcpyHostToDevice, e->st_copy));
+                CK(cudaMemcpyAsync(dbuf[(i + 1) & 1], yuv + (size_t)(i + 1) * bytes, fsz * cnt(i + 1), cudaMemcpyHostToDevice, e->st_copy));
                 CK(cudaEventRecord(e->ev_copy[(i + 1) & 1], e->st_copy));
             }
             CK(cudaStreamWaitEvent(e->st, e->ev_copy[i & 1], 0));
             const uint8_t *d = nullptr; size_t len = 0;
-            rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, dbuf[i & 1], e->batch_frames, e->frames_encoded, &d, &len);
+            rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, dbuf[i & 1], cnt(i), e->frames_encoded, &d, &len);
             if (rc) return rc;
             const size_t at = e->outq.size();
             e->outq.resize(at + len);
-            CK(cudaMemcpy(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost));
-            e->frames_encoded += e->batch_frames;
+            CK(cudaMemcpyAsync(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost, e->st));
+            CK(cudaStreamSynchronize(e->st));
+            e->frames_encoded += cnt(i);
         }
-        yuv += (size_t)nb * bytes; nframes -= nb * e->batch_frames;
+        yuv += (size_t)direct * fsz; nframes -= direct;
     }
     while (nframes > 0) {
         const long take = std::min(nframes, e->batch_frames - e->staged_frames);

@@ -100,12 +100,15 @@ __device__ __forceinline__ void fdct8(const int x[8], int o[8]) {
 #define W5 1609u
 #define W6 1108u
 #define W7 565u
-__device__ __forceinline__ int sx18(int v) { return (int)((uint32_t)v << 14) >> 14; }
+// (Measured and rejected: issuing constant arithmetic shifts as IMAD.HI to move them to the FMA pipe made K1
+// 2-4 % slower - IMAD.HI is not full rate.)
+template <int S> __device__ __forceinline__ int asr(int v) { return v >> S; }
+__device__ __forceinline__ int sx18(int v) { return asr<14>((int)((uint32_t)v << 14)); }
 
 // Chen-Wang rows (RTL:849-904): 13-bit in, 18-bit out.  The RTL computes in 32-bit registers that
 // wrap; unsigned arithmetic reproduces that without relying on signed overflow.
 typedef uint32_t u32;
-__device__ __forceinline__ int sra(u32 v, int s) { return (int)v >> s; }
+#define sra(v, s) asr<s>((int)(v))
 __device__ __forceinline__ void idct_row(const int a[8], int r[8]) {
     u32 x0 = ((u32)a[0] << 11) + 128u, x1 = (u32)a[4] << 11, x2 = a[6], x3 = a[2], x4 = a[1], x5 = a[7], x6 = a[5], x7 = a[3], x8;
     x8 = W7 * (x4 + x5); x4 = x8 + (W1 - W7) * x4; x5 = x8 - (W1 + W7) * x5;
@@ -366,7 +369,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                 sd = __reduce_add_sync(FULL, sd);
                 const int cy = i / 3 - 1, cx = i % 3 - 1;
                 bool dis = (cx < 0 && xn) || (cx > 0 && xp) || (cy < 0 && yn) || (cy > 0 && yp);   // RTL:1757-1760
-                key[i] = (dis || sd >= 4096u) ? 8191 : (int)sd;
+                // {f_over, f_diff}: any key >= 4096 loses against the intra key (<= 4095) and against every valid
+                // candidate, and ties among keys >= 4096 never decide anything, so the overflowed SAD itself
+                // serves as its own "disabled" key (RTL:1784-1785, 1795-1804)
+                key[i] = dis ? 0x10000 : (int)sd;
             }
             // intra key: pixel sum + sum|pixel-mean|, 16 bit, saturated to 4095 (RTL:1600,1662,1744,1776-1777,1791)
             uint32_t S = __reduce_add_sync(FULL, sad4(c0, 0, sad4(c1, 0, 0)));
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                 if (maybe) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const int C = (o[i] + 2048) >> 12;                           // RTL:2058
+                        const int C = asr<12>(o[i] + 2048);                          // RTL:2058
                         const int yq = (abs(C) + 2) >> (4 + Q);                      // RTL:2070
                         const int sgn = (C >> 31) | 1;
                         if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const QEntry qe = qt[i * 8 + v];
-                    const int C = (o[i] + 2048) >> 12;
+                    const int C = asr<12>(o[i] + 2048);
                     const int yq = (int)__umulhi((uint32_t)(abs(C) + (int)qe.off) >> Q, qe.recip);   // RTL:2072 (exact division)
                     const int q = yq * ((C >> 31) | 1);
                     s.res[tile][qe.zz] = (int16_t)q;

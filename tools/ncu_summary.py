@@ -91,20 +91,24 @@ def main():
     ie, ws = h.index('Instructions Executed'), h.index('Warp Stall Sampling (All Samples)')
     rows = [r for r in blk['rows'][1:] if len(r) == len(h)][:len(seq)]
     tot, alu, smp, ops = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
+    regops = collections.defaultdict(collections.Counter)
     for (ln, txt), r in zip(seq, rows):
         c = int(r[ie]); reg = region(ln)
         tot[reg] += c; smp[reg] += int(r[ws])
         op = re.sub(r'^@!?U?P\w+\s+', '', txt).split()[0].split('.')[0]
         ops[op] += c
+        regops[reg][op] += c
         if op in ALU:
             alu[reg] += c
     first = int(rows[0][ie]) or 1                     # executions of the first instruction = warps launched
     grid_warps = first
+    units = collections.Counter(int(r[ie]) for r in rows).most_common(1)[0][0] or 1   # modal execution count = work items (macroblocks)
     T, A, S = sum(tot.values()), sum(alu.values()), max(sum(smp.values()), 1)
     print('\n## region table for %s (%s), SASS instrs matched: %d' % (kern, blk['name'][:60], len(rows)))
-    print('   warp-instructions executed: %d total, %d on the ALU pipe; first-instruction executions (warps): %d' % (T, A, grid_warps))
+    print('   warp-instructions executed: %d total, %d on the ALU pipe; warps: %d; work items (modal count): %d -> %.0f instr, %.0f ALU per item' % (T, A, grid_warps, units, T / units, A / units))
     for reg in sorted(tot, key=lambda k: int(re.match(r'L(\d+)', k).group(1)) if k[0] == 'L' else 0):
         print('   %-72s %5.1f%% instr  %5.1f%% alu  %5.1f%% stall-samples' % (reg, 100 * tot[reg] / T, 100 * alu[reg] / max(A, 1), 100 * smp[reg] / S))
+        print('       per work item: ' + ', '.join('%s %.1f' % (k, v / units) for k, v in regops[reg].most_common(10)))
     print('   opcode mix (%% of executed): ' + ', '.join('%s %.1f' % (k, 100 * v / T) for k, v in ops.most_common(16)))
 
 
