@@ -144,9 +144,9 @@ __device__ __forceinline__ void idct_col(const int a[8], int o[8]) {
 // One pipeline stage = everything TMA brings in for one macroblock.  Every member is a dense TMA box
 // and starts on a 128-byte boundary.
 struct __align__(128) StageSmem {
-    uint32_t curY[16][4];            // current luma block, 16 rows x 16 B                (box 16x16 of plane Y)
-    uint32_t curU[16][4];            // current 4:4:4 U block                             (box 16x16 of plane U)
-    uint32_t curV[16][4];            //                 V
+    uint32_t curY[16][4];            // current luma block, 16 rows x 16 B      } one box 16x16x3 over the planes
+    uint32_t curU[16][4];            // current 4:4:4 U block                   } Y,U,V of the input frame
+    uint32_t curV[16][4];            //                 V                        }
     // TMA needs the inner coordinate of a box to be a multiple of 16 bytes (probed: tools/tma_probe.cu),
     // so the windows start at the 16-byte boundary at or below the first byte that is needed.
     uint32_t winC[2][16][8];         // chroma windows: rows 8by-4..8by+11, 32 bytes from (8bx-8)&~15     (2 boxes 32x16)
@@ -225,16 +225,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         StageSmem &S = s.st[stg];
         const uint32_t bar = smem_u32(&bars[stg]);
         mbar_expect_tx(bar, TX_BYTES);
-        tma_load_4d(smem_u32(S.curY), &tm_in, m.bx * 16, m.by * 16, 0, n, bar);
-        tma_load_4d(smem_u32(S.curU), &tm_in, m.bx * 16, m.by * 16, 1, n, bar);
-        tma_load_4d(smem_u32(S.curV), &tm_in, m.bx * 16, m.by * 16, 2, n, bar);
+        tma_load_4d(smem_u32(S.curY), &tm_in, m.bx * 16, m.by * 16, 0, n, bar);       // one 16x16x3 box: curY, curU, curV
         if (PFRAME) {
             // out-of-frame parts of a box are zero-filled by TMA; they only ever feed candidates the border
             // rule disables (RTL:1642-1645, 1757-1760).  (RTL:1350-1425, 1613-1629 fetch the same windows.)
             const int cx0 = (m.bx * 8 - 8) & ~15;
             tma_load_3d(smem_u32(S.winY), &tm_refY, m.bx * 16 - 16, m.by * 16 - (R + 1), m.g, bar);
-            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);
-            tma_load_4d(smem_u32(S.winC[1]), &tm_refC, cx0, m.by * 8 - 4, 1, m.g, bar);
+            tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);   // one 32x16x2 box: U and V windows
         }
     };
     MbPos cur = decode(gwarp);
@@ -601,7 +598,7 @@ bool m2v_make_tmaps(M2VBatch &b) {
     const int WROWS = 18 + 4 * b.g.VL;
     {
         const cuuint64_t d[4] = {W, H, 3, (cuuint64_t)b.F}, st[3] = {W, ysz, 3 * ysz};
-        const cuuint32_t box[4] = {16, 16, 1, 1};
+        const cuuint32_t box[4] = {16, 16, 3, 1};
         if (!make_map(&b.tm_in, (void *)b.in, 4, d, st, box)) return false;
     }
     for (int k = 0; k < 2; k++) {
@@ -609,7 +606,7 @@ bool m2v_make_tmaps(M2VBatch &b) {
         const cuuint32_t boxy[3] = {48, (cuuint32_t)WROWS, 1};
         if (!make_map(&b.tm_refY[k], b.recon[k], 3, dy, sy, boxy)) return false;
         const cuuint64_t dc[4] = {CWp, CH, 2, G}, sc[3] = {CWp, CWp * CH, b.fsz420};
-        const cuuint32_t boxc[4] = {32, 16, 1, 1};
+        const cuuint32_t boxc[4] = {32, 16, 2, 1};
         if (!make_map(&b.tm_refC[k], b.recon[k] + ysz, 4, dc, sc, boxc)) return false;
     }
     return true;

@@ -29,12 +29,19 @@ def test_readme_size_pin_and_clip_hashes(ob):
         out = ob.encode(fr, W // 16, H // 16, 23, XL=7, YL=6, VL=3, Q=2)     # TB:23-24,98-99,106
         assert len(out) == meta[name]['length']
         assert hashlib.sha256(out).hexdigest() == meta[name]['sha256']
+        import mpeg2_parser                                       # and it is well-formed ISO 13818-2 to the last bit
+        st = mpeg2_parser.parse(out)
+        assert (st['width'], st['height'], len(st['pictures'])) == (W, H, fr.shape[0])
+        assert all(len(pic['mbs']) == (W // 16) * (H // 16) for pic in st['pictures'])
 
 
 def test_golden_clipA(ob):
     fr = np.fromfile(os.path.join(GOLD, 'clipA_64x64.yuv'), dtype=np.uint8).reshape(5, 3, 64, 64)
     want = open(os.path.join(GOLD, 'clipA_64x64.m2v'), 'rb').read()
     assert ob.encode(fr, 4, 4, 23, XL=7, YL=6, VL=3, Q=2) == want
+    import mpeg2_parser
+    st = mpeg2_parser.parse(want)
+    assert [p['type'] for p in st['pictures']] == [1, 2, 2, 2, 2] and st['frame_rate_code'] == 2
 
 
 def test_header_known_answers(ob):
@@ -206,3 +213,36 @@ def test_range_encoding_is_gop_local(ob, synth):
     parts = ob.seq_header(6, 4) + ob.encode_range(fr[0:4], 0, 6, 4, 3) + ob.encode_range(fr[4:10], 4, 6, 4, 3)
     n = len(parts) + 4
     assert whole == parts + b'\x00\x00\x01\xb7' + bytes(32 * (n // 32 + 1) - n)
+
+
+@pytest.mark.parametrize('gen,P,Q', [('S1', 3, 2), ('S2', 2, 1), ('S3', 5, 4), ('S4', 7, 3)])
+def test_stream_parses_as_iso_13818_2_and_round_trips(ob, synth, gen, P, Q):
+    """Independent check of the entropy layer: a parser written from the ISO/IEC 13818-2 syntax (tests/
+    mpeg2_parser.py) must walk the oracle's stream to the end and recover exactly the macroblock types, motion
+    vectors, coded block patterns and quantised levels the oracle says it coded (RTL:2718-2847 vs 13818-2 6.2.5)."""
+    import mpeg2_parser
+    W, H, n = 96, 64, 7
+    fr = synth.GENERATORS[gen](99, n, W, H)
+    data, dbg = ob.encode(fr, W // 16, H // 16, P, VL=3, Q=Q, want_dbg=True)
+    s = mpeg2_parser.parse(data)
+    assert (s['width'], s['height']) == (W, H) and len(s['pictures']) == n
+    nmb = (W // 16) * (H // 16)
+    for f, pic in enumerate(s['pictures']):
+        k = f % (P + 1)
+        assert pic['type'] == (1 if k == 0 else 2) and pic['temporal_reference'] == k
+        assert (pic['gop'] is not None) == (k == 0)
+        if k == 0:
+            assert pic['gop']['closed_gop'] == 1 and pic['gop']['pictures'] == f % 24 and pic['gop']['seconds'] == (f // 24) % 60
+        assert len(pic['mbs']) == nmb
+        for i, mb in enumerate(pic['mbs']):
+            j = f * nmb + i
+            assert mb['qsc'] == 1 << Q
+            inter = bool(dbg['mb_inter'][j])
+            assert mb['type'].startswith('mc') == inter
+            lv = np.array(mb['levels'], dtype=np.int64)
+            if inter:
+                assert mb['mv'] == [int(dbg['mb_mvx'][j]), int(dbg['mb_mvy'][j])]
+            else:
+                lv[:, 0] -= 512                                  # intra_dc_precision 10 bit: predictor reset value
+            assert mb['cbp'] == int(dbg['mb_cbp'][j])
+            assert (lv == dbg['coefs'][j]).all(), (f, i)
