@@ -130,7 +130,7 @@ def main():
         # simulator, so the timed CPU arm is the oracle port on all host threads, one GOP per thread per step.
         if rank != 0:
             return
-        nthr = min(cores, 64)
+        nthr = min(cores, 256)
         cpu_oracle_throughput(cfg, nthr, a.q, steps=1)
         v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=max(1, a.steps))
         print(json.dumps({
@@ -152,6 +152,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'                       # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=dev)
     if cfg['scaling'] == 'weak':
         F = max(gop, cfg['frames'] // gop * gop)
@@ -214,6 +215,38 @@ def main():
     else:
         total_stream = 32 * ((34 + body_len + 4) // 32 + 1)
 
+    # ---- end-to-end through the streaming C-ABI with host buffers (every rank streams its own block) ----
+    e2e = None
+    if not a.no_e2e and F:
+        Fe = max(gop, min(a.e2e_frames // gop * gop, F))
+        host = torch.empty((Fe, 3, H, W), dtype=torch.uint8).pin_memory()
+        host.copy_(frames[:Fe])
+        hnp = host.numpy()
+        e2 = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q)
+        def one():
+            e2.begin(mbw, mbh, P); e2.push_frames(hnp); e2.sequence_stop()
+            data, last = e2.drain(cap=64 << 20)
+            assert last
+            return len(data)
+        for _ in range(2):
+            nbytes = one()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(a.steps):
+            nbytes = one()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t1) / a.steps
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te[0])
+        e2e = {'value': round(world * Fe * W * H / dt / 1e6, 2), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': world * Fe * 3 * W * H,
+               'd2h_bytes_per_step': world * nbytes, 'frames_per_gpu': Fe, 'ms_per_step': round(dt * 1e3, 3),
+               'api': 'm2v_begin / m2v_push_frames(pinned host) / m2v_stop / m2v_drain, one stream per rank, max over ranks',
+               'note': 'H2D of 3 B/pixel dominates; PCIe ceiling per GPU on this box is ~54 GB/s = ~18 Gpixel/s (profiles/r01_h2d_probe.txt)'}
+        e2.close()
+        del host
+
     if rank != 0:
         dist.barrier(); dist.destroy_process_group()
         return
@@ -243,36 +276,9 @@ def main():
     except Exception:
         pass
 
-    # ---- end-to-end through the streaming C-ABI with host buffers ----
-    e2e = None
-    if not a.no_e2e and world == 1:
-        Fe = max(gop, min(a.e2e_frames // gop * gop, F))
-        host = torch.empty((Fe, 3, H, W), dtype=torch.uint8).pin_memory()
-        host.copy_(frames[:Fe])
-        hnp = host.numpy()
-        e2 = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q)
-        def one():
-            e2.begin(mbw, mbh, P); e2.push_frames(hnp); e2.sequence_stop()
-            data, last = e2.drain(cap=64 << 20)
-            assert last
-            return len(data)
-        for _ in range(2):
-            nbytes = one()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for _ in range(a.steps):
-            nbytes = one()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t1) / a.steps
-        e2e = {'value': round(Fe * W * H / dt / 1e6, 2), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': Fe * 3 * W * H,
-               'd2h_bytes_per_step': nbytes, 'frames': Fe, 'ms_per_step': round(dt * 1e3, 3),
-               'api': 'm2v_begin / m2v_push_frames(pinned host) / m2v_stop / m2v_drain',
-               'note': 'H2D of 3 B/pixel dominates; PCIe ceiling on this box is ~54 GB/s = ~18 Gpixel/s (profiles/r01_h2d_probe.txt)'}
-        e2.close()
-
     cpu = None
     if not a.no_cpu and world == 1:
-        nthr = min(cores, 64)
+        nthr = min(cores, 256)
         v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=1)
         cpu = {'value': round(v, 3), 'unit': 'Mpixel/s', 'cores': nthr, 'kind': 'port',
                'sample': '%d frames (%d per host thread, GOP-parallel) of the workload clip, %.1f s' % (fr, fr // nthr, dt)}
