@@ -306,12 +306,18 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             // the end.  The border rule (RTL:1642-1645) is warp-uniform in dy and per-lane in dx.
             uint32_t best = 0xFFFFFFFFu;
             const int dx = (lane & 15) - R;
-            const int dylo = (by == 0) ? R : 0, dyhi = (by == p.mbh - 1) ? R : 2 * R;
-#pragma unroll
-            for (int dyi = 0; dyi <= 2 * R; dyi++) {
-                if (dyi < dylo || dyi > dyhi) continue;
+            auto fold = [&](int dyi) {
                 const uint32_t tot = acc[dyi] + __shfl_xor_sync(FULL, acc[dyi], 16);
                 best = min(best, tot * 1024u + (uint32_t)(((2 * R - dyi) << 5) + R - dx));
+            };
+            if (by != 0) {                                   // dy < 0 is forbidden in the top block row (two warp-uniform branches)
+#pragma unroll
+                for (int dyi = 0; dyi < R; dyi++) fold(dyi);
+            }
+            fold(R);
+            if (by != p.mbh - 1) {                           // dy > 0 is forbidden in the bottom block row
+#pragma unroll
+                for (int dyi = R + 1; dyi <= 2 * R; dyi++) fold(dyi);
             }
             if (lane > 2 * R || (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0)) best = 0xFFFFFFFFu;
             best = __reduce_min_sync(FULL, best);
