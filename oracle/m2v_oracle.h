@@ -6,12 +6,16 @@
  * and bench.py's cpu_baseline / --impl reference legs as the checker and the timed CPU baseline.
  * The product (fpga-mpeg2-encoder_b200/) never includes, links or calls anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" at bit level.  The reference ships no golden bitstreams and
- * no Verilog simulator exists in the build image (iverilog/vvp/verilator absent), so the RTL
- * itself cannot be executed here.  The only published result is the output size of
- * SIM/data.zip:1440x704.yuv with the testbench defaults, 775 456 bytes (README.md:748); this
- * oracle reproduces that size exactly (tests/test_oracle_pins.py) and its streams decode with
- * FFmpeg's mpeg2video decoder.  See DESIGN.md "Oracle".
+ * PARITY STATUS: PINNED AGAINST THE REFERENCE ITSELF.  The reference ships no golden bitstreams and no
+ * Verilog simulator exists in the build image or on the GPU box, so oracle/vl2c.py translates the
+ * reference RTL (read where it lies under /root/reference, never copied) into a cycle-based C++ model
+ * under oracle/_ref/ which oracle/rtl_tb.cpp drives exactly like SIM/tb_mpeg2encoder.v.  That model
+ * (a) reproduces the only number the reference publishes - 775 456 bytes for SIM/data.zip:1440x704.yuv
+ * with the testbench defaults (README.md:748) - and (b) is byte-identical to this oracle on all three
+ * testbench clips run back to back, on every VECTOR_LEVEL x Q_LEVEL, on the S1-S4 clip classes, with
+ * mid-frame stops, input bubbles, size clamps and GOP lengths up to 255 (tests/test_rtl_pin.py; committed
+ * RTL-written fixtures in tests/golden/).  Caveat, stated once: the simulator that executes the RTL is this
+ * repository's own translator, not iverilog.  See DESIGN.md "Oracle".
  */
 #ifndef M2V_ORACLE_H
 #define M2V_ORACLE_H

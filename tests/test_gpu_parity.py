@@ -44,11 +44,29 @@ def _compare(pkg, ob, frames, P, VL=3, Q=2, XL=7, YL=7, partial_px4=0):
     return got
 
 
-def test_golden_fixture(pkg, ob):
-    fr = np.fromfile(os.path.join(GOLD, 'clipA_64x64.yuv'), dtype=np.uint8).reshape(5, 3, 64, 64)
-    want = open(os.path.join(GOLD, 'clipA_64x64.m2v'), 'rb').read()
+def test_golden_fixtures_written_by_the_rtl(pkg):
+    """tests/golden/*.m2v are outputs of the reference RTL itself (oracle/vl2c.py model, make_golden.py); the
+    CUDA path must reproduce them without any oracle in the loop"""
+    import json
+    meta = json.load(open(os.path.join(GOLD, 'rtl_fixtures.json')))
+    for name, m in meta.items():
+        fr = np.fromfile(os.path.join(GOLD, name + '.yuv'), dtype=np.uint8).reshape(m['frames'], 3, m['H'], m['W'])
+        want = open(os.path.join(GOLD, name + '.m2v'), 'rb').read()
+        enc = pkg.Mpeg2Encoder(XL=m['XL'], YL=m['YL'], VECTOR_LEVEL=m['VL'], Q_LEVEL=m['Q'])
+        assert enc.encode_sequence(fr, m['P'], partial_px4=m['partial_px4']) == want, name
+        enc.close()
+
+
+def test_cuda_equals_rtl_model_directly(pkg, synth):
+    """where a prebuilt oracle/_ref model travelled to this box: CUDA vs the RTL model, no oracle involved"""
+    import rtl_ref_binding as rb
+    if not rb.available(7, 6, 3, 2):
+        pytest.skip('no oracle/_ref model on this box')
+    r = rb.RtlRef(7, 6, 3, 2)
     enc = pkg.Mpeg2Encoder(XL=7, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2)
-    assert enc.encode_sequence(fr, 23) == want
+    for seed, (W, H, n, P) in enumerate([(160, 96, 6, 3), (64, 64, 9, 23), (288, 208, 3, 1)]):
+        fr = synth.s1_pan(100 + seed, n, W, H)
+        assert enc.encode_sequence(fr, P) == r.sequence(fr, W // 16, H // 16, P)
 
 
 def test_intra_only_config2_shape(pkg, ob, synth):
