@@ -628,6 +628,8 @@ class Gen:
         # memories (large arrays) written by NBA use a write queue instead of a shadow copy
         queue = nba and s.size > 4096
         for tg in targets:
+            if tg.startswith('n_') and s.dims and not queue:
+                out.append('%sd_%s = true;' % (ind, s.cname))          # shadow array touched: commit it at the end of the clock
             if s.dims:
                 ic = self.idx_code(s, idxs)
                 ref = 'AT(%s,%s,%d)' % (tg, ic, s.size)
@@ -700,7 +702,9 @@ class Gen:
             o.append('  ' + self.decl_code(s))
             if s.nba:
                 if s.size > 4096: o.append('  std::vector<std::pair<i64,u64> > q_%s;' % s.cname)
-                else: o.append('  ' + self.decl_code(s, 'n_'))
+                else:
+                    o.append('  ' + self.decl_code(s, 'n_'))
+                    if s.dims: o.append('  bool d_%s = false;' % s.cname)
         # functions
         for f in self.funcs.values():
             _, name, signed, rg, decls, body = f
@@ -756,6 +760,7 @@ class Gen:
                 if s.size > 4096:
                     o.append('    for (size_t i_ = 0; i_ < q_%s.size(); i_++) if (INR(q_%s[i_].first,%d)) %s[q_%s[i_].first] = q_%s[i_].second;' % (s.cname, s.cname, s.size, s.cname, s.cname, s.cname))
                     o.append('    q_%s.clear();' % s.cname)
+                elif s.dims: o.append('    if (d_%s) { %s = n_%s; d_%s = false; }' % (s.cname, s.cname, s.cname, s.cname))
                 else: o.append('    %s = n_%s;' % (s.cname, s.cname))
         o.append('    comb();')
         o.append('  }')
