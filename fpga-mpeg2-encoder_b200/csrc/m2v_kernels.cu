@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         }
     };
     MbPos cur = decode(gwarp);
+    // the stride between a warp's macroblocks is constant, so the next position is the current one plus a
+    // fixed (GOP, row, column) step with at most one carry per field - no divisions inside the loop
+    const MbPos step = decode(nwarps);
     if (lane == 0) {
         mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -248,7 +251,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
 #pragma unroll 1
     for (unsigned idx = gwarp; idx < p.total; idx += nwarps, stg ^= 1, cur = nxt) {
     if (idx + nwarps < p.total) {
-        nxt = decode(idx + nwarps);
+        nxt.bx = cur.bx + step.bx; nxt.by = cur.by + step.by; nxt.g = cur.g + step.g;
+        if (nxt.bx >= p.mbw) { nxt.bx -= p.mbw; nxt.by++; }
+        if (nxt.by >= p.mbh) { nxt.by -= p.mbh; nxt.g++; }
         if (lane == 0) { fence_proxy_async(); issue(nxt, stg ^ 1); }
     }
     const int g = cur.g, by = cur.by, bx = cur.bx;

@@ -181,3 +181,21 @@ def test_config3_and_config4_sizes_sample_gop(pkg, ob, synth):
     want = ob.encode_range(host, 16, W // 16, H // 16, P)
     l2 = enc.encode_gops_host(fr.data_ptr() + 16 * fsz, 3, 16, W // 16, H // 16, P, out)
     assert out[:l2].tobytes() == want
+
+
+def test_testbench_replay_cli(pkg, ob, synth, tmp_path):
+    """csrc/m2venc_tb.cpp = C++ host replaying TB:142-274 through the C-ABI: several videos back to back on one
+    instance (TB:150), one frame per push like the testbench's frame loop, and the 4-pixel port (-push4)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), 'm2venc_tb')
+    if not os.path.exists(exe):
+        pytest.skip('m2venc_tb not built')
+    vids = [(synth.s1_pan(1, 5, 96, 64), 96, 64), (synth.s4_edges(2, 3, 64, 80), 64, 80)]
+    args = []
+    for i, (fr, W, H) in enumerate(vids):
+        fr.tofile(str(tmp_path / ('v%d.yuv' % i)))
+        args += [str(tmp_path / ('v%d.yuv' % i)), str(W), str(H), str(tmp_path / ('v%d.m2v' % i))]
+    for extra in ([], ['-push4']):
+        subprocess.check_call([exe, '-XL', '6', '-YL', '6', '-VL', '3', '-Q', '2', '-P', '23'] + extra + args, stdout=subprocess.DEVNULL)
+        for i, (fr, W, H) in enumerate(vids):
+            assert open(str(tmp_path / ('v%d.m2v' % i)), 'rb').read() == ob.encode(fr, W // 16, H // 16, 23, XL=6, YL=6, VL=3, Q=2)
