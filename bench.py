@@ -45,33 +45,67 @@ def alg_bytes_per_pixel(p):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (a query takes well under
+    a millisecond, so a 100 ms timed region still gets dozens of samples); nvidia-smi as the fallback."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.reasons, self.max_mhz = index, [], False, set(), None
+        self.active = threading.Event()                         # set only while a timed region is running
+        self.query_s = []
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            ids = [int(x) for x in vis.split(',')] if vis and all(x.strip().isdigit() for x in vis.split(',')) else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if ids and index < len(ids) else index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
+            if not self.active.wait(0.01):
+                continue
+            if self.nvml is not None:
+                try:
+                    tq = time.perf_counter()
+                    self.samples.append(int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    r = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    for name, bit in self.BITS:
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.query_s.append(time.perf_counter() - tq)
+                except Exception:
+                    pass
+                time.sleep(0.001)
+                continue
             try:
                 o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
                                    capture_output=True, text=True, timeout=5).stdout.strip().split(',')
-                self.samples.append([x.strip() for x in o])
+                o = [x.strip() for x in o]
+                if o and o[0].isdigit():
+                    self.samples.append(int(o[0]))
+                if len(o) > 1 and o[1].isdigit():
+                    self.max_mhz = max(self.max_mhz or 0, int(o[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), o[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.samples)}
+        sm = sorted(self.samples)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi',
+                'ms_per_query': round(1e3 * sum(self.query_s) / len(self.query_s), 2) if self.query_s else None,
+                'sampled': 'during the timed regions only (device-resident steps and the e2e steps)'}
 
 
 def cpu_oracle_throughput(cfg, nthreads, q, steps=1):
@@ -166,7 +200,7 @@ def main():
         r = rtl_reference_throughput(cfg, min(nthr, 32), a.q, steps=max(1, min(a.steps, 2)))
         if r is not None:
             v, dt, fr = r; kind = 'reference'
-            sample = '%d frames (1 per host thread, 32 threads, one RTL instance per thread, 64 clocks per macroblock) of the workload clip per step' % fr
+            sample = '%d frames (1 per host thread, %d threads, one RTL instance per thread, 64 clocks per macroblock) of the workload clip per step' % (fr, fr)
         else:
             v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=max(1, a.steps)); kind = 'port'
             sample = '%d frames (%d per host thread) of the workload clip per step' % (fr, fr // nthr)
@@ -218,7 +252,7 @@ def main():
         if F:
             ptr, body_len = enc.encode_gops_device(frames.data_ptr(), F, n0, mbw, mbh, P)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local); sampler.start(); sampler.active.set()
     l0 = enc.launch_count
     dev_ms = 0.0; kms = [0.0] * 5
     t0 = time.perf_counter()
@@ -230,7 +264,7 @@ def main():
             dev_ms += k[4]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    sampler.stop_flag = True; sampler.join()
+    sampler.active.clear()
     launches = enc.launch_count - l0
     tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)       # device time, max over ranks
     if world > 1:
@@ -268,11 +302,13 @@ def main():
         for _ in range(2):
             nbytes = one()
         barrier()
+        sampler.active.set()
         t1 = time.perf_counter()
         for _ in range(a.steps):
             nbytes = one()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t1) / a.steps
+        sampler.active.clear()
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -284,6 +320,7 @@ def main():
         e2.close()
         del host
 
+    sampler.stop_flag = True; sampler.join()
     if rank != 0:
         dist.barrier(); dist.destroy_process_group()
         return
@@ -320,7 +357,7 @@ def main():
         r = rtl_reference_throughput(cfg, min(nthr, 32), a.q, steps=1)
         if r is not None:
             cpu = {'value': round(r[0], 3), 'unit': 'Mpixel/s', 'cores': min(nthr, 32), 'kind': 'reference',
-                   'sample': '%d frames (1 per host thread, 32 threads; the reference RTL via oracle/vl2c.py, one instance per thread), %.1f s' % (r[2], r[1]),
+                   'sample': '%d frames (1 per host thread, %d threads; the reference RTL via oracle/vl2c.py, one instance per thread), %.1f s' % (r[2], r[2], r[1]),
                    'oracle_port_mpixel_s': round(pv, 3)}
         else:
             cpu = {'value': round(pv, 3), 'unit': 'Mpixel/s', 'cores': nthr, 'kind': 'port',

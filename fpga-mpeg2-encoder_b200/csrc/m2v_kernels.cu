@@ -168,6 +168,7 @@ struct K1Args {
     int W, H, mbw, mbh, nmb, P, Q, t, CWp;                  // CWp = chroma row stride of the recon buffers (16-byte multiple)
     unsigned fsz420;                                        // bytes per reconstructed frame = W*H + 2*CWp*H/2
     unsigned total;                                         // ngops_t * nmb macroblocks in this launch
+    int write_rec;                                          // 0 for the last frame of a GOP: its reconstruction is never read
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -492,14 +493,20 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             // acts; the branch on `inter` is warp-uniform and hoisted out of the coefficient loop.
             if (inter) {
                 if (maybe) {
+                    // the same bound per coefficient: -thr < B < thr  =>  level 0 (and dequantised value 0), so
+                    // only the few coefficients outside it run the quantiser (a real branch, not predication)
+                    const int thr = 4096 * ((1 << (4 + Q)) - 2) - 2048;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const int C = asr<12>(o[i] + 2048);                          // RTL:2058
-                        const int yq = (abs(C) + 2) >> (4 + Q);                      // RTL:2070
-                        const int sgn = (C >> 31) | 1;
-                        if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
-                        const int m = min(yq ? ((2 * yq + 1) << Q) : 0, 2047);       // RTL:2134-2137
-                        o[i] = m * sgn;
+                        int dq = 0;
+                        if ((uint32_t)(o[i] + thr - 1) >= (uint32_t)(2 * thr - 1)) {
+                            const int C = asr<12>(o[i] + 2048);                      // RTL:2058
+                            const int yq = (abs(C) + 2) >> (4 + Q);                  // RTL:2070
+                            const int sgn = (C >> 31) | 1;
+                            if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
+                            dq = min(yq ? ((2 * yq + 1) << Q) : 0, 2047) * sgn;      // RTL:2134-2137
+                        }
+                        o[i] = dq;
                     }
                 } else {
 #pragma unroll
@@ -563,18 +570,22 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
 
     // ---- outputs: reconstruction (next frame's reference), levels, record -----------------------
     {
-        uint8_t *oY = p.rec + (size_t)g * p.fsz420;
-        const int y = lane >> 1, half = lane & 1, tile = (y >> 3) * 2 + half;
-        *(uint2 *)(oY + (size_t)(Y0 + y) * W + X0 + 8 * half) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
-        if (lane < 16) {
-            const int comp = lane >> 3, cyy = lane & 7;
-            *(uint2 *)(oY + ysz + (size_t)comp * CWp * (p.H >> 1) + (size_t)(by * 8 + cyy) * CWp + bx * 8) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
+        if (p.write_rec) {                                       // warp-uniform: the last frame of a GOP is nobody's reference
+            uint8_t *oY = p.rec + (size_t)g * p.fsz420;
+            const int y = lane >> 1, half = lane & 1, tile = (y >> 3) * 2 + half;
+            *(uint2 *)(oY + (unsigned)((Y0 + y) * W + X0 + 8 * half)) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
+            if (lane < 16) {
+                const int comp = lane >> 3, cyy = lane & 7;
+                *(uint2 *)(oY + (unsigned)(ysz + (comp * (p.H >> 1) + by * 8 + cyy) * CWp + bx * 8)) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
+            }
         }
         const size_t mbi = (size_t)n * p.nmb + mb;
         uint2 *dst = (uint2 *)(p.coefs + mbi * 384);
         const uint2 *src = (const uint2 *)&s.res[0][0];
+        // a tile whose cbp bit is clear holds no level and K2 never reads it (RTL:2799, 2804, 2828): not written
 #pragma unroll
-        for (int k = 0; k < 3; k++) dst[lane + 32 * k] = src[lane + 32 * k];
+        for (int k = 0; k < 3; k++)
+            if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = src[lane + 32 * k];
         if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
     }
     __syncwarp();
@@ -648,6 +659,7 @@ void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
     a.W = b.g.W; a.H = b.g.H; a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.Q = b.g.Q; a.t = t;
     a.CWp = b.CWp; a.fsz420 = (unsigned)b.fsz420;
     a.total = (unsigned)(ngops_t * b.g.nmb);
+    a.write_rec = t < b.g.P;
     const int refk = (t & 1) ^ 1;
     if (t == 0) { launch_k1_t<1, false>(a, b, refk, st); return; }
     switch (b.g.VL) {

@@ -87,7 +87,8 @@ int  m2v_sequence_header(int mbw, int mbh, uint8_t out34[34]);
  * padding up to the next 32-byte multiple with the RTL's "always one more word" rule. */
 int  m2v_finish_stream(uint8_t *buf, size_t len, size_t cap, size_t *total);
 
-/* Debug taps used by the parity tests (device -> host copies of the last encode_gops call). */
+/* Debug taps used by the parity tests (device -> host copies of the last encode_gops call).  A tile
+ * of `coefs` is only meaningful where the macroblock's cbp bit is set: uncoded tiles are not written. */
 int  m2v_debug_copy(m2v_encoder *e, uint32_t *mbinfo, int16_t *coefs, long nframes_times_nmb);
 /* Kernel launch counter (bench.py "gpu_launches") and device time in ms (CUDA events on the
  * launching stream) of the last encode_gops call: idx 0 = all mb_encode (K1) launches, 1 = vlc count,

@@ -109,6 +109,19 @@ def main():
     for reg in sorted(tot, key=lambda k: int(re.match(r'L(\d+)', k).group(1)) if k[0] == 'L' else 0):
         print('   %-72s %5.1f%% instr  %5.1f%% alu  %5.1f%% stall-samples' % (reg, 100 * tot[reg] / T, 100 * alu[reg] / max(A, 1), 100 * smp[reg] / S))
         print('       per work item: ' + ', '.join('%s %.1f' % (k, v / units) for k, v in regops[reg].most_common(10)))
+    if os.environ.get('NCU_LINES'):
+        # per source line: executed warp-instructions per work item and the opcodes behind them
+        perline = collections.defaultdict(collections.Counter)
+        for (ln, txt), r in zip(seq, rows):
+            op = re.sub(r'^@!?U?P\w+\s+', '', txt).split()[0].split('.')[0]
+            perline[ln][op] += int(r[ie])
+        print('   per source line (instr per work item):')
+        for ln in sorted(perline, key=lambda k: (k is None, k)):
+            c = perline[ln]; t = sum(c.values())
+            if t / units < 0.5:
+                continue
+            text = src[ln - 1].strip()[:70] if ln else '(inlined helper / other file)'
+            print('     %5s %7.1f  %-70s %s' % (ln, t / units, text, ', '.join('%s %.0f' % (k, v / units) for k, v in c.most_common(5))))
     print('   opcode mix (%% of executed): ' + ', '.join('%s %.1f' % (k, 100 * v / T) for k, v in ops.most_common(16)))
 
 
