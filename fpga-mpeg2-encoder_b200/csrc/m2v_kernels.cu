@@ -155,9 +155,9 @@ struct __align__(128) StageSmem {
 struct __align__(128) WarpSmem {
     StageSmem st[2];                 // double buffer: TMA fills st[k^1] while st[k] is being encoded
     uint32_t curC[2][8][2];          // current 4:2:0 chroma blocks
-    int16_t res[6][64];              // residual, later the zig-zag levels
-    uint8_t pred[6][64];             // prediction, later the reconstruction
-};                                   // 7936 bytes; the two mbarriers of each warp live after the warps' areas
+    int16_t res[8][64];              // residual, later the zig-zag levels; tiles 6,7 are all-zero dummies that keep lanes
+    uint8_t pred[8][64];             // prediction, later the reconstruction          16..31 busy in the chroma round
+};                                   // 8320 bytes; the two mbarriers of each warp live after the warps' areas
 // the transform scratch (4 tile slots x TSTR words) aliases winC+winY of the stage being encoded:
 // the windows are dead once the prediction has been formed.
 static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratch must fit in the window area");
@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);   // one 32x16x2 box: U and V windows
         }
     };
+    reinterpret_cast<uint2 *>(&s.res[6][0])[lane] = make_uint2(0, 0);          // dummy tiles: zero residual, zero prediction
+    reinterpret_cast<uint32_t *>(&s.pred[6][0])[lane] = 0;
     MbPos cur = decode(gwarp);
     // the stride between a warp's macroblocks is constant, so the next position is the current one plus a
     // fixed (GOP, row, column) step with at most one carry per field - no divisions inside the loop
@@ -451,16 +453,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     __syncwarp();
 
     // ---- transform / quantise / scan / reconstruct.  Round 0: luma tiles on 32 lanes (tile = lane>>3,
-    //      vector = lane&7); round 1: chroma tiles on 16 lanes.  (RTL:2029-2077, 2128-2356, 2452-2467)
+    //      vector = lane&7); round 1: chroma tiles on lanes 0..15 while lanes 16..31 run the same code on two
+    //      all-zero dummy tiles (no predicate, no divergence, warp syncs with the constant full mask - a run-time
+    //      mask makes the compiler guard every sync with MATCH/REDUX/VOTE).  (RTL:2029-2077, 2128-2356, 2452-2467)
     int cbp = 0;
     const int Q = p.Q;
 #pragma unroll 1
     for (int round = 0; round < 2; round++) {
-        const bool act = (round == 0) || lane < 16;
         const int tile = round * 4 + (lane >> 3), v = lane & 7;
         int32_t *tt = tmp + (lane >> 3) * TSTR;
         int x[8], o[8];
-        if (act) {                                               // rows: A = R * DCTM^T (RTL:2029-2036)
+        {                                                        // rows: A = R * DCTM^T (RTL:2029-2036)
             uint4 rv = *(const uint4 *)&s.res[tile][v * 8];
             x[0] = (int16_t)(rv.x & 0xFFFF); x[1] = (int32_t)rv.x >> 16; x[2] = (int16_t)(rv.y & 0xFFFF); x[3] = (int32_t)rv.y >> 16;
             x[4] = (int16_t)(rv.z & 0xFFFF); x[5] = (int32_t)rv.z >> 16; x[6] = (int16_t)(rv.w & 0xFFFF); x[7] = (int32_t)rv.w >> 16;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         }
         __syncwarp();
         bool nzl = false, maybe = true;
-        if (act) {                                               // columns: B = DCTM * A (RTL:2054-2057)
+        {                                                        // columns: B = DCTM * A (RTL:2054-2057)
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
             fdct8(x, o);
@@ -486,8 +489,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                 *(uint4 *)&s.res[tile][v * 8] = make_uint4(0, 0, 0, 0);
             }
         }
-        __syncwarp();                                            // zero fill complete before any level is scattered
-        if (act) {                                               // round, quantise, scan, dequantise
+        __syncwarp();                                        // zero fill complete before any level is scattered
+        {                                                        // round, quantise, scan, dequantise
             const int b00 = o[0];
             // |C| <= 255*512*512/4096 = 16320, so every level is < 2047 and the RTL's clip (RTL:2075) never
             // acts; the branch on `inter` is warp-uniform and hoisted out of the coefficient loop.
@@ -508,10 +511,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                         }
                         o[i] = dq;
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) o[i] = 0;
-                }
+                }                                                // else: no level in this column, o[] is not used again
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -534,35 +534,42 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                 nzl = true;
             }
         }
-        __syncwarp();                                            // all column reads of A done before overwrite
-        if (act) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) tt[i * 8 + v] = o[i];
-        }
-        const uint32_t nzm = __ballot_sync(FULL, act && nzl);
+        const uint32_t nzm = __ballot_sync(FULL, nzl);
         if (round == 0) { for (int k = 0; k < 4; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (32 >> k) : 0; }
-        else { for (int k = 0; k < 2; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (2 >> k) : 0; }
-        __syncwarp();
+        else { for (int k = 0; k < 2; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (2 >> k) : 0; }      // bits 16..31: the dummies
         // A tile whose levels are all zero reconstructs to exactly the prediction (all-zero input gives
         // (128)>>8 = 0 after the row pass and (8192)>>14 = 0 after the column pass), so its inverse
-        // transform is skipped; the decision is per 8-lane group.
-        const bool inv = act && ((nzm >> (8 * (lane >> 3))) & 0xFF);
-        if (inv) {                                               // inverse rows (in place)
+        // transform is skipped; the decision is per 8-lane group, and when no tile of the round holds a level
+        // (the usual case in a well-predicted picture) the whole inverse part is one uniform branch.
+        if (nzm) {
+            const bool inv = (nzm >> (8 * (lane >> 3))) & 0xFF;
+            __syncwarp();                                    // all column reads of A done before overwrite
+            if (inv) {
+                if (inter && !maybe) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) x[j] = tt[v * 8 + j];
-            idct_row(x, o);
+                    for (int i = 0; i < 8; i++) o[i] = 0;
+                }
 #pragma unroll
-            for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
-        }
-        __syncwarp();
-        if (inv) {                                               // inverse columns, add prediction, clip (RTL:2352)
+                for (int i = 0; i < 8; i++) tt[i * 8 + v] = o[i];
+            }
+            __syncwarp();
+            if (inv) {                                           // inverse rows (in place)
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
-            idct_col(x, o);
+                for (int j = 0; j < 8; j++) x[j] = tt[v * 8 + j];
+                idct_row(x, o);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                int r = (int)s.pred[tile][i * 8 + v] + o[i];
-                s.pred[tile][i * 8 + v] = (uint8_t)max(0, min(255, r));
+                for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
+            }
+            __syncwarp();
+            if (inv) {                                           // inverse columns, add prediction, clip (RTL:2352)
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
+                idct_col(x, o);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    int r = (int)s.pred[tile][i * 8 + v] + o[i];
+                    s.pred[tile][i * 8 + v] = (uint8_t)max(0, min(255, r));
+                }
             }
         }
         __syncwarp();
@@ -765,6 +772,9 @@ __device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__
         for (int ch = 0; ch < 4; ch++) {
             const uint4 a = __ldg(src + 2 * ch), b = __ldg(src + 2 * ch + 1);
             const uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+            // most 16-level chunks of a coded tile are empty (the levels sit at the low frequencies): skip them before
+            // building the mask.  The first chunk of an intra tile always codes its DC (RTL:2808-2821).
+            if ((((w0 | w1) | (w2 | w3)) | ((w4 | w5) | (w6 | w7))) == 0 && (inter || ch != 0)) continue;
             uint32_t m = 0;
             m |= ((w0 & 0xFFFFu) ? 1u : 0u) | ((w0 >> 16) ? 2u : 0u);
             m |= ((w1 & 0xFFFFu) ? 4u : 0u) | ((w1 >> 16) ? 8u : 0u);
