@@ -57,6 +57,7 @@ struct m2v_encoder {
     DevBuf<int16_t> d_coefs;
     DevBuf<uint32_t> d_mbinfo, d_mb_bits, d_mb_off, d_slice_off, d_frame_bytes, d_out;
     DevBuf<unsigned long long> d_frame_off;
+    DevBuf<unsigned> d_k1ctr; unsigned k1_seq = 0;      // K1 work counters (see M2VBatch::k1_ctr)
     // last encode_gops chunk (debug taps) and statistics
     long last_F = 0; int last_nmb = 0;
     long launches = 0;
@@ -83,6 +84,8 @@ extern "C" int m2v_create(int XL, int YL, int VL, int Q, m2v_encoder **out) {
         cudaDeviceSynchronize() != cudaSuccess) {           // table uploads ride the legacy stream: finish them before any launch on e->st
         delete e; return M2V_ECUDA;
     }
+    if (e->d_k1ctr.reserve(2) != cudaSuccess || cudaMemset(e->d_k1ctr.p, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) { m2v_destroy(e); return M2V_ECUDA; }
     for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
     cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking);
     for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
@@ -99,7 +102,7 @@ extern "C" void m2v_destroy(m2v_encoder *e) {
     for (int i = 0; i < 2; i++) if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
     e->d_in.release(); e->d_in2.release(); e->d_recon0.release(); e->d_recon1.release(); e->d_body.release(); e->d_coefs.release();
     e->d_mbinfo.release(); e->d_mb_bits.release(); e->d_mb_off.release(); e->d_slice_off.release();
-    e->d_frame_bytes.release(); e->d_out.release(); e->d_frame_off.release();
+    e->d_frame_bytes.release(); e->d_out.release(); e->d_frame_off.release(); e->d_k1ctr.release();
     delete e;
 }
 
@@ -155,13 +158,15 @@ static int encode_chunk(m2v_encoder *e, int mbw, int mbh, int P, const uint8_t *
     b.recon[0] = e->d_recon0.p; b.recon[1] = P ? e->d_recon1.p : e->d_recon0.p;
     b.coefs = e->d_coefs.p; b.mbinfo = e->d_mbinfo.p; b.mb_bits = e->d_mb_bits.p; b.mb_off = e->d_mb_off.p;
     b.slice_off = e->d_slice_off.p; b.frame_bytes = e->d_frame_bytes.p; b.frame_off = e->d_frame_off.p; b.out_words = nullptr;
+    b.k1_ctr = e->d_k1ctr.p;
+    if (G * b.g.nmb >= M2V_K1_MAX_MBS) { snprintf(e->err, sizeof e->err, "chunk too large for one K1 launch"); return M2V_EINVAL; }
     e->last_F = F; e->last_nmb = b.g.nmb;
     if (!m2v_make_tmaps(b)) { snprintf(e->err, sizeof e->err, "cuTensorMapEncodeTiled failed"); return M2V_ECUDA; }
 
     if (e->timing) CK(cudaEventRecord(e->ev[0], e->st));
     for (int t = 0; t <= P && t < F; t++) {                       // frame t of every GOP that has one
         const long ng = (F - t + gop - 1) / gop;
-        m2v_launch_k1(b, t, ng, e->st); e->launches++;
+        m2v_launch_k1(b, t, ng, e->k1_seq++, e->st); e->launches++;
     }
     if (e->timing) CK(cudaEventRecord(e->ev[1], e->st));
     m2v_launch_k2(b, false, e->st); e->launches++;

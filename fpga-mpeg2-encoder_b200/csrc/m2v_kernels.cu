@@ -169,6 +169,8 @@ struct K1Args {
     unsigned fsz420;                                        // bytes per reconstructed frame = W*H + 2*CWp*H/2
     unsigned total;                                         // ngops_t * nmb macroblocks in this launch
     int write_rec;                                          // 0 for the last frame of a GOP: its reconstruction is never read
+    unsigned *ctr, *ctr_next;                               // work counter of this launch (zero on entry) / of the next one (zeroed here)
+    uint32_t mw, mh;                                        // ceil(2^32/mbw), ceil(2^32/mbh): index -> (GOP, row, column) without divisions
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,8 +192,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm,
                  ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
-// Persistent warps: warp w encodes macroblocks w, w+nwarps, w+2*nwarps, ... of the launch; the TMA
-// loads of the next macroblock are in flight while the current one is encoded.
+// Persistent warps with DYNAMIC work distribution: a warp's first macroblock is its own global index, every
+// further one comes from an atomic counter, fetched one macroblock ahead so that the TMA loads of the next
+// macroblock are in flight while the current one is encoded and the atomic's round trip hides behind the encode.
+// (With a static stride the warps of an SM sub-partition finish far apart - the scheduler favours some of them -
+// and the tail runs at a fraction of the occupancy: ncu showed 4.5 of 6 resident warps active on average.)
 template <int VL, bool PFRAME>
 __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
                                                                const __grid_constant__ CUtensorMap tm_refY,
@@ -211,13 +216,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     const int W = p.W, CWp = p.CWp;
     const size_t ysz = (size_t)W * p.H;
 
-    // macroblock index -> (GOP, block row, block column): decoded once per macroblock (all lanes), reused
-    // by the TMA issue of the prefetch and by the encode one iteration later
+    // macroblock index -> (GOP, block row, block column).  floor(n/d) == umulhi(n, ceil(2^32/d)) for n*d < 2^32:
+    // d <= 128 and a launch has fewer than 2^25 macroblocks (m2v_launch_k1 checks; tests/test_host_logic.py)
     struct MbPos { int g, by, bx; };
     auto decode = [&](unsigned idx) {
         MbPos m;
-        const unsigned g = idx / (unsigned)p.nmb, mb = idx - g * p.nmb;
-        m.g = (int)g; m.by = (int)(mb / (unsigned)p.mbw); m.bx = (int)mb - m.by * p.mbw;
+        const unsigned rowg = __umulhi(idx, p.mw), g = __umulhi(rowg, p.mh);
+        m.bx = (int)(idx - rowg * (unsigned)p.mbw); m.by = (int)(rowg - g * (unsigned)p.mbh); m.g = (int)g;
         return m;
     };
     // one elected lane arms the stage's mbarrier with the byte count and issues the TMA boxes
@@ -237,27 +242,27 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     };
     reinterpret_cast<uint2 *>(&s.res[6][0])[lane] = make_uint2(0, 0);          // dummy tiles: zero residual, zero prediction
     reinterpret_cast<uint32_t *>(&s.pred[6][0])[lane] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
+    // lane 0 draws the next index; the value is only looked at one macroblock later
+    auto draw = [&]() { unsigned v = 0; if (lane == 0) v = nwarps + atomicAdd(p.ctr, 1u); return v; };
     MbPos cur = decode(gwarp);
-    // the stride between a warp's macroblocks is constant, so the next position is the current one plus a
-    // fixed (GOP, row, column) step with at most one carry per field - no divisions inside the loop
-    const MbPos step = decode(nwarps);
     if (lane == 0) {
         mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
         issue(cur, 0);
     }
-    __syncwarp();
+    unsigned nidx = __shfl_sync(FULL, draw(), 0);                              // index of the macroblock after this one
     uint32_t phase = 0;
     int stg = 0;
-    MbPos nxt = cur;
 #pragma unroll 1
-    for (unsigned idx = gwarp; idx < p.total; idx += nwarps, stg ^= 1, cur = nxt) {
-    if (idx + nwarps < p.total) {
-        nxt.bx = cur.bx + step.bx; nxt.by = cur.by + step.by; nxt.g = cur.g + step.g;
-        if (nxt.bx >= p.mbw) { nxt.bx -= p.mbw; nxt.by++; }
-        if (nxt.by >= p.mbh) { nxt.by -= p.mbh; nxt.g++; }
+    for (;; stg ^= 1) {
+    const bool more = nidx < p.total;
+    const MbPos nxt = decode(nidx);
+    unsigned drawn = 0;
+    if (more) {
         if (lane == 0) { fence_proxy_async(); issue(nxt, stg ^ 1); }
+        drawn = draw();
     }
     const int g = cur.g, by = cur.by, bx = cur.bx;
     const unsigned mb = (unsigned)(by * p.mbw + bx);
@@ -596,6 +601,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
     }
     __syncwarp();
+    if (!more) break;
+    cur = nxt;
+    nidx = __shfl_sync(FULL, drawn, 0);
     }   // persistent loop
 }
 
@@ -659,7 +667,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
     k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, smem, st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
 }
 
-void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
+void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st) {
     K1Args a;
     a.rec = b.recon[t & 1];
     a.coefs = b.coefs; a.mbinfo = b.mbinfo;
@@ -667,6 +675,8 @@ void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st) {
     a.CWp = b.CWp; a.fsz420 = (unsigned)b.fsz420;
     a.total = (unsigned)(ngops_t * b.g.nmb);
     a.write_rec = t < b.g.P;
+    a.ctr = b.k1_ctr + (seq & 1); a.ctr_next = b.k1_ctr + ((seq & 1) ^ 1);
+    a.mw = (uint32_t)((0x100000000ull + b.g.mbw - 1) / b.g.mbw); a.mh = (uint32_t)((0x100000000ull + b.g.mbh - 1) / b.g.mbh);
     const int refk = (t & 1) ^ 1;
     if (t == 0) { launch_k1_t<1, false>(a, b, refk, st); return; }
     switch (b.g.VL) {

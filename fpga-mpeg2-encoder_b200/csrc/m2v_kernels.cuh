@@ -32,11 +32,15 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     uint32_t *frame_bytes;     // [F]       slice-area bytes of the frame
     unsigned long long *frame_off; // [F+1] byte offset of each frame in the body; [F] = total
     uint32_t *out_words;       // body, big-endian bit order packed into bytes
+    unsigned *k1_ctr;          // [2] work counters of K1's dynamic macroblock distribution; launch `seq` uses [seq&1] and
+                               // zeroes the other one for the launch after it (both zero before the first launch)
 };
+#define M2V_K1_MAX_MBS (1l << 25)   // macroblocks per K1 launch: bound of the division-free index decode
 
 bool m2v_make_tmaps(M2VBatch &b);
-// K1: one warp per macroblock; step t = frame index inside every GOP of the batch
-void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, cudaStream_t st);
+// K1: one warp per macroblock; step t = frame index inside every GOP of the batch; seq = running number of the K1
+// launches on this stream (selects the work counter)
+void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st);
 // K2: one warp per macroblock; count = bit lengths only, write = emit into out_words
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st);
 // K3: slice/frame/batch scans of the bit lengths; then headers

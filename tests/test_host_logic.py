@@ -68,6 +68,21 @@ def test_reciprocal_division_is_exact():
         assert ((n * r) >> np.uint64(32) == n // np.uint64(w)).all(), w
 
 
+def test_index_decode_is_exact():
+    """K1 turns a drawn macroblock index into (GOP, row, column) with umulhi(n, ceil(2^32/d)), d = macroblocks per row /
+    rows per frame (4..128): exact for every n below 2^25 = M2V_K1_MAX_MBS, the per-launch bound the host enforces."""
+    rng = np.random.default_rng(5)
+    for d in range(4, 129):
+        m = np.uint64((0x100000000 + d - 1) // d)
+        k = np.arange(0, (1 << 25) // d + 1, dtype=np.uint64) * np.uint64(d)          # every multiple of d, and its neighbours
+        n = np.concatenate([k, k[1:] - np.uint64(1), k + np.uint64(1), rng.integers(0, 1 << 25, 200000, dtype=np.uint64),
+                            np.arange((1 << 25) - 70000, 1 << 25, dtype=np.uint64)])
+        n = n[n < (1 << 25)]
+        assert ((n * m) >> np.uint64(32) == n // np.uint64(d)).all(), d
+    src = open(os.path.join(ROOT, 'fpga-mpeg2-encoder_b200', 'csrc', 'm2v_kernels.cuh')).read()
+    assert '#define M2V_K1_MAX_MBS (1l << 25)' in src
+
+
 def test_gop_partition(pkg):
     from fpga_mpeg2_encoder_b200 import sharding
     for nfr, P, world in ((512, 15, 8), (1000, 15, 8), (22, 3, 3), (5, 7, 4), (16, 0, 5)):
