@@ -294,11 +294,15 @@ def main():
         host.copy_(frames[:Fe])
         hnp = host.numpy()
         e2 = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q)
+        sink = np.empty(64 << 20, np.uint8)                      # the caller's stream buffer (m2v_drain copies the words into it)
         def one():
             e2.begin(mbw, mbh, P); e2.push_frames(hnp); e2.sequence_stop()
-            data, last = e2.drain(cap=64 << 20)
-            assert last
-            return len(data)
+            n, last = e2.drain_into(sink)
+            while not last:                                      # a stream longer than the buffer: keep pulling (the words are consumed)
+                k, last = e2.drain_into(sink)
+                assert k or last
+                n += k
+            return n
         for _ in range(2):
             nbytes = one()
         barrier()

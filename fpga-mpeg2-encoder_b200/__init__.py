@@ -156,6 +156,12 @@ class Mpeg2Encoder:
         rc = self._ck(lib().m2v_pull(self._h, w, C.byref(last)))
         return (bytes(w), bool(last.value)) if rc == 1 else None
 
+    def drain_into(self, buf):
+        """m2v_drain straight into a caller-owned uint8 numpy buffer (no intermediate copies): -> (bytes written, last)"""
+        n = C.c_size_t(0); l = C.c_int(0)
+        self._ck(lib().m2v_drain(self._h, buf.ctypes.data, buf.size, C.byref(n), C.byref(l)))
+        return n.value, bool(l.value)
+
     def drain(self, cap=1 << 24):
         """all available whole words -> (bytes, last)"""
         chunks = []

@@ -37,6 +37,33 @@ template <typename T> struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Output word queue in PINNED host memory: the device->host copies of the bodies run at PCIe rate instead of
+// going through the driver's bounce buffer for pageable memory.
+struct PinnedQ {
+    uint8_t *p = nullptr; size_t n = 0, cap = 0;
+    size_t size() const { return n; }
+    uint8_t *data() { return p; }
+    void clear() { n = 0; }
+    bool resize(size_t want) {
+        if (want > cap) {
+            size_t nc = std::max(want + want / 2, (size_t)1 << 20);
+            uint8_t *q = nullptr;
+            if (cudaHostAlloc((void **)&q, nc, cudaHostAllocDefault) != cudaSuccess) return false;
+            if (n) memcpy(q, p, n);
+            if (p) cudaFreeHost(p);
+            p = q; cap = nc;
+        }
+        n = want;
+        return true;
+    }
+    void erase_front(size_t k) { memmove(p, p + k, n - k); n -= k; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+};
+#define QRESIZE(q, want)                                                                  \
+    do {                                                                                  \
+        if (!(q).resize(want)) { snprintf(e->err, sizeof e->err, "cudaHostAlloc of the output queue failed"); return M2V_ENOMEM; } \
+    } while (0)
+
 struct m2v_encoder {
     int XL, YL, VL, Q;
     int dev;
@@ -50,7 +77,7 @@ struct m2v_encoder {
     long staged_frames = 0;
     size_t px_in_frame = 0;            // pixels of the partially pushed frame (push4)
     long batch_frames = 0;             // flush threshold (whole GOPs)
-    std::vector<uint8_t> outq; size_t out_rd = 0;
+    PinnedQ outq; size_t out_rd = 0;
     // device buffers
     DevBuf<uint8_t> d_in, d_in2, d_recon0, d_recon1, d_body;
     cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr};
@@ -102,7 +129,7 @@ extern "C" void m2v_destroy(m2v_encoder *e) {
     for (int i = 0; i < 2; i++) if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
     e->d_in.release(); e->d_in2.release(); e->d_recon0.release(); e->d_recon1.release(); e->d_body.release(); e->d_coefs.release();
     e->d_mbinfo.release(); e->d_mb_bits.release(); e->d_mb_off.release(); e->d_slice_off.release();
-    e->d_frame_bytes.release(); e->d_out.release(); e->d_frame_off.release(); e->d_k1ctr.release();
+    e->d_frame_bytes.release(); e->d_out.release(); e->d_frame_off.release(); e->d_k1ctr.release(); e->outq.release();
     delete e;
 }
 
@@ -284,7 +311,7 @@ static int start_if_idle(m2v_encoder *e) {
     if (e->busy) return M2V_OK;
     if (e->mbw == 0 || e->ended) { snprintf(e->err, sizeof e->err, "push before begin"); return M2V_ESTATE; }
     e->busy = true;
-    e->outq.resize(34);
+    QRESIZE(e->outq, 34);
     return m2v_sequence_header(e->mbw, e->mbh, e->outq.data());
 }
 
@@ -300,7 +327,7 @@ static int flush_staged(m2v_encoder *e) {
     int rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, e->d_in.p, e->staged_frames, e->frames_encoded, &d, &len);
     if (rc) return rc;
     const size_t at = e->outq.size();
-    e->outq.resize(at + len);
+    QRESIZE(e->outq, at + len);
     CK(cudaMemcpyAsync(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
     e->frames_encoded += e->staged_frames;
@@ -358,7 +385,7 @@ extern "C" int m2v_push_frames(m2v_encoder *e, const uint8_t *yuv, long nframes)
             rc = m2v_encode_gops_device(e, e->mbw, e->mbh, e->P, dbuf[i & 1], cnt(i), e->frames_encoded, &d, &len);
             if (rc) return rc;
             const size_t at = e->outq.size();
-            e->outq.resize(at + len);
+            QRESIZE(e->outq, at + len);
             CK(cudaMemcpyAsync(e->outq.data() + at, d, len, cudaMemcpyDeviceToHost, e->st));
             CK(cudaStreamSynchronize(e->st));
             e->frames_encoded += cnt(i);
@@ -389,7 +416,7 @@ extern "C" int m2v_stop(m2v_encoder *e) {
     }
     int rc = flush_staged(e); if (rc) return rc;
     const size_t len = e->outq.size();
-    e->outq.resize(32 * ((len + 4) / 32 + 1));
+    QRESIZE(e->outq, 32 * ((len + 4) / 32 + 1));
     size_t tot = 0;
     rc = m2v_finish_stream(e->outq.data(), len, e->outq.size(), &tot); if (rc) return rc;
     e->ended = true;
@@ -407,7 +434,7 @@ extern "C" int m2v_drain(m2v_encoder *e, uint8_t *dst, size_t cap, size_t *n, in
     const bool fin = e->ended && e->out_rd == e->outq.size();
     if (last) *last = fin && take > 0;
     if (fin) { e->busy = false; e->ended = false; e->mbw = 0; e->outq.clear(); e->out_rd = 0; }   // back to IDLE (RTL:1045-1047)
-    else if (e->out_rd > (64u << 20)) { e->outq.erase(e->outq.begin(), e->outq.begin() + e->out_rd); e->out_rd = 0; }
+    else if (e->out_rd > (64u << 20)) { e->outq.erase_front(e->out_rd); e->out_rd = 0; }
     return M2V_OK;
 }
 
