@@ -162,7 +162,35 @@ def rtl_reference_throughput(cfg, nthreads, q, steps=1, frames_per_thread=1):
     return frames * W * H / best / 1e6, best, frames
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and so, by first touch, its pinned staging memory) to the CPUs NVML reports as
+    local to its GPU: with 8 ranks streaming 3 B/pixel each, host buffers on the wrong socket halve the H2D rate."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        ids = [int(x) for x in vis.split(',')] if vis and all(x.strip().isdigit() for x in vis.split(',')) else None
+        h = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if ids and index < len(ids) else index)
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 1) + 63) // 64)
+        cpus = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
+    # stdout carries the single JSON line and nothing else: whatever a library prints to file descriptor 1 (NCCL's
+    # version banner, for one) is sent to stderr, and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + '\n'); real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -204,14 +232,14 @@ def main():
         else:
             v, dt, fr = cpu_oracle_throughput(cfg, nthr, a.q, steps=max(1, a.steps)); kind = 'port'
             sample = '%d frames (%d per host thread) of the workload clip per step' % (fr, fr // nthr)
-        print(json.dumps({
+        emit({
             'impl': 'reference', 'metric': 'Mpixel/s', 'value': round(v, 3), 'unit': 'Mpixel/s', 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': round(dt * 1e3, 3), 'higher_is_better': True, 'scaling': cfg['scaling'],
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config,
             'cpu_baseline': {'value': round(v, 3), 'unit': 'Mpixel/s', 'cores': (min(nthr, 32) if kind == 'reference' else nthr), 'kind': kind, 'sample': sample,
                              'oracle_port_mpixel_s': round(port[0], 3)},
             'e2e': {'value': round(v, 3), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'fps': round(v * 1e6 / (W * H), 2)}))
+            'fps': round(v * 1e6 / (W * H), 2)})
         return
 
     import numpy as np
@@ -220,10 +248,10 @@ def main():
     import __graft_entry__ as ge
     pkg = ge.load_package(); synth = ge.load_synth()
     from fpga_mpeg2_encoder_b200 import sharding
+    ncpu_local = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'                       # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=dev)
     if cfg['scaling'] == 'weak':
         F = max(gop, cfg['frames'] // gop * gop)
@@ -320,6 +348,7 @@ def main():
         e2e = {'value': round(world * Fe * W * H / dt / 1e6, 2), 'unit': 'Mpixel/s', 'h2d_bytes_per_step': world * Fe * 3 * W * H,
                'd2h_bytes_per_step': world * nbytes, 'frames_per_gpu': Fe, 'ms_per_step': round(dt * 1e3, 3),
                'api': 'm2v_begin / m2v_push_frames(pinned host) / m2v_stop / m2v_drain, one stream per rank, max over ranks',
+               'host_cpus_per_rank': ncpu_local,
                'note': 'H2D of 3 B/pixel dominates; PCIe ceiling per GPU on this box is ~54 GB/s = ~18 Gpixel/s (profiles/r01_h2d_probe.txt)'}
         e2.close()
         del host
@@ -374,7 +403,7 @@ def main():
             'bytes_per_pixel_out': round(body_len / max(F * W * H, 1), 5),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': sampler.summary(),
             'published_yardstick': {'fpga_mpixel_s': 268, 'fpga_fps_1920x1152': 121, 'source': 'reference README.md:22 (Kintex-7 FPGA; context only)'}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
