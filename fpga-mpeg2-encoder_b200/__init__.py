@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     'm2v_create', 'm2v_destroy', 'm2v_last_error', 'm2v_begin', 'm2v_push4', 'm2v_push_frames', 'm2v_stop',
     'm2v_busy', 'm2v_pull', 'm2v_drain', 'm2v_encode_gops_device', 'm2v_encode_gops_host',
     'm2v_sequence_header', 'm2v_finish_stream', 'm2v_debug_copy', 'm2v_launch_count', 'm2v_kernel_ms',
-    'm2v_set_timing',
+    'm2v_set_timing', 'm2v_set_limits',
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
         L.m2v_launch_count.argtypes = [vp]; L.m2v_launch_count.restype = C.c_long
         L.m2v_kernel_ms.argtypes = [vp, vp]
         L.m2v_set_timing.argtypes = [vp, ip]
+        L.m2v_set_limits.argtypes = [vp, C.c_long, C.c_long]
         _lib = L
     return _lib
 
@@ -225,6 +226,10 @@ class Mpeg2Encoder:
 
     def set_timing(self, on):
         self._ck(lib().m2v_set_timing(self._h, int(on)))
+
+    def set_limits(self, batch_frames=0, chunk_frames=0):
+        """test knob (m2v_set_limits): frames per streaming batch / per encode_gops chunk; 0 = automatic"""
+        self._ck(lib().m2v_set_limits(self._h, int(batch_frames), int(chunk_frames)))
 
     def kernel_ms(self):
         a = (C.c_float * 5)()

@@ -77,6 +77,7 @@ struct m2v_encoder {
     long staged_frames = 0;
     size_t px_in_frame = 0;            // pixels of the partially pushed frame (push4)
     long batch_frames = 0;             // flush threshold (whole GOPs)
+    long force_batch = 0, force_chunk = 0;   // m2v_set_limits (0 = automatic)
     PinnedQ outq; size_t out_rd = 0;
     // device buffers
     DevBuf<uint8_t> d_in, d_in2, d_recon0, d_recon1, d_body;
@@ -135,6 +136,11 @@ extern "C" void m2v_destroy(m2v_encoder *e) {
 
 extern "C" const char *m2v_last_error(const m2v_encoder *e) { return e ? e->err : "null handle"; }
 extern "C" long m2v_launch_count(const m2v_encoder *e) { return e ? e->launches : 0; }
+extern "C" int m2v_set_limits(m2v_encoder *e, long batch_frames, long chunk_frames_) {
+    if (!e || batch_frames < 0 || chunk_frames_ < 0) return M2V_EINVAL;
+    e->force_batch = batch_frames; e->force_chunk = chunk_frames_;
+    return M2V_OK;
+}
 extern "C" int m2v_set_timing(m2v_encoder *e, int en) { if (!e) return M2V_EINVAL; e->timing = en != 0; return M2V_OK; }
 extern "C" int m2v_kernel_ms(const m2v_encoder *e, float ms[5]) { if (!e) return M2V_EINVAL; memcpy(ms, e->kms, sizeof e->kms); return M2V_OK; }
 
@@ -220,10 +226,11 @@ static int encode_chunk(m2v_encoder *e, int mbw, int mbh, int P, const uint8_t *
     return M2V_OK;
 }
 
-static long chunk_frames(const m2v_encoder *, int mbw, int mbh, int P) {
+static long chunk_frames(const m2v_encoder *e, int mbw, int mbh, int P) {
     // bound the level buffer (768 B per macroblock) to ~6 GiB per chunk, whole GOPs
     const size_t per_frame = (size_t)mbw * mbh * 768;
     long f = (long)((6ull << 30) / per_frame);
+    if (e->force_chunk > 0) f = std::min(f, e->force_chunk);
     const long gop = P + 1;
     f = std::max(gop, f / gop * gop);
     return f;
@@ -303,6 +310,7 @@ extern "C" int m2v_begin(m2v_encoder *e, int xs, int ys, int P, int *mbw, int *m
     while ((size_t)g * gop * fsz < ((size_t)64 << 20)) g++;       // and >= 64 MiB of input, so per-batch overheads stay small
     while (g > 1 && (size_t)g * gop * fsz > ((size_t)1 << 30)) g--;
     e->batch_frames = g * gop;
+    if (e->force_batch > 0) e->batch_frames = std::max(gop, std::min(e->batch_frames, e->force_batch / gop * gop));
     // the RTL arms on the first i_en (RTL:1060-1065); the header is emitted then
     return M2V_OK;
 }

@@ -94,6 +94,11 @@ int  m2v_debug_copy(m2v_encoder *e, uint32_t *mbinfo, int16_t *coefs, long nfram
  * launching stream) of the last encode_gops call: idx 0 = all mb_encode (K1) launches, 1 = vlc count,
  * 2 = scans + size read-back + headers, 3 = vlc write, 4 = first launch -> last kernel end. */
 long m2v_launch_count(const m2v_encoder *e);
+/* Test knob: overrides the sizes the library picks by itself - the streaming flush threshold (frames per batch of
+ * m2v_push*; rounded down to whole GOPs, at least one) and the frames per internal chunk of m2v_encode_gops_* -
+ * so that the multi-batch / multi-chunk paths can be driven with small clips.  0 = automatic.  The stream does not
+ * depend on either value (closed GOPs, RTL:2645-2656). */
+int  m2v_set_limits(m2v_encoder *e, long batch_frames, long chunk_frames);
 int  m2v_kernel_ms(const m2v_encoder *e, float ms[5]);
 int  m2v_set_timing(m2v_encoder *e, int enable);
 

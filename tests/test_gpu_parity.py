@@ -200,6 +200,60 @@ def test_config5_maximum_size(pkg, ob, synth):
     enc.close()
 
 
+def test_streaming_batches_and_chunks_are_invisible(pkg, ob, synth):
+    """the stream does not depend on how the library cuts the work (closed GOPs, RTL:2645-2656): the double-buffered
+    multi-batch path of m2v_push_frames, the staged path (frame-by-frame pushes, trailing partial GOP, unfinished last
+    frame) and the multi-chunk path of m2v_encode_gops_*, all forced to tiny sizes with m2v_set_limits"""
+    W, H, P, n = 96, 64, 3, 23                                   # 5 whole GOPs + 3 frames
+    fr = synth.s1_pan(77, n, W, H)
+    want = ob.encode(fr, W // 16, H // 16, P, XL=6, YL=6)
+    for batch in (4, 8, 12):                                     # 1, 2, 3 GOPs per batch
+        enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+        enc.set_limits(batch_frames=batch, chunk_frames=4)
+        assert enc.encode_sequence(fr, P) == want, batch
+        enc.begin(W // 16, H // 16, P)                           # same handle, frame-by-frame pushes (staged path)
+        for k in range(n):
+            enc.push_frames(fr[k:k + 1])
+        enc.sequence_stop()
+        assert enc.drain()[0] == want, batch
+        enc.begin(W // 16, H // 16, P)                           # 9 frames, then 14 more
+        enc.push_frames(fr[:9]); enc.push_frames(fr[9:]); enc.sequence_stop()
+        assert enc.drain()[0] == want, batch
+        enc.close()
+    want_p = ob.encode(fr, W // 16, H // 16, P, XL=6, YL=6, partial_px4=333)
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    enc.set_limits(batch_frames=4, chunk_frames=4)
+    assert enc.encode_sequence(fr, P, partial_px4=333) == want_p
+    enc.close()
+    import torch
+    d = torch.from_numpy(fr[:20]).cuda()
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    out = np.zeros(4 << 20, np.uint8)
+    for chunk in (0, 4, 8):                                      # automatic (one chunk), 1 GOP, 2 GOPs per chunk
+        enc.set_limits(chunk_frames=chunk)
+        ln = enc.encode_gops_host(d.data_ptr(), 20, 0, W // 16, H // 16, P, out)
+        assert pkg.finish_stream(pkg.sequence_header(W // 16, H // 16) + out[:ln].tobytes()) == ob.encode(fr[:20], W // 16, H // 16, P, XL=6, YL=6), chunk
+    enc.close()
+
+
+def test_streaming_full_size_multi_batch(pkg, ob, synth):
+    """1920x1152 I+15P through the streaming C-ABI at the default thresholds: one GOP (106 MB) per batch, so 3 GOPs + 5
+    frames cross the double-buffered H2D pipeline three times and end in the staged path - against the oracle, GOP by GOP"""
+    import threading
+    W, H, P, n = 1920, 1152, 15, 53
+    fr = synth.s1_pan(9, n, W, H)
+    enc = pkg.Mpeg2Encoder(XL=7, YL=7)
+    got = enc.encode_sequence(fr, P)
+    enc.close()
+    bodies = [None] * 4
+    def work(g):
+        bodies[g] = ob.encode_range(fr[16 * g:16 * (g + 1)], 16 * g, W // 16, H // 16, P)
+    th = [threading.Thread(target=work, args=(g,)) for g in range(4)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert got == pkg.finish_stream(pkg.sequence_header(W // 16, H // 16) + b''.join(bodies))
+
+
 def test_testbench_replay_cli(pkg, ob, synth, tmp_path):
     """csrc/m2venc_tb.cpp = C++ host replaying TB:142-274 through the C-ABI: several videos back to back on one
     instance (TB:150), one frame per push like the testbench's frame loop, and the 4-pixel port (-push4)."""
