@@ -379,7 +379,21 @@ def main():
                 'phase_ms_per_step': {'k1_mb_encode': round(k1_ms, 3), 'k2_vlc_count': round(kms[1] / a.steps, 3),
                                       'k3_scans_k4_headers': round(kms[2] / a.steps, 3), 'k2_vlc_write': round(kms[3] / a.steps, 3)}}
     try:
-        roofline['traffic'] = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json'))).get('dram_bytes_per_launch')
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json')))
+        roofline['traffic'] = prof.get('dram_bytes_per_launch')
+        # the roofline that actually binds K1: the integer ALU pipe (one warp instruction per 2 clocks per SM sub-partition).
+        # Instruction counts per macroblock come from the committed ncu capture, time and clock are measured live.
+        ap = prof.get('alu_pipe')
+        clk = sampler.summary()['sm_mhz']
+        if ap and clk and VL == 3 and k1_ms > 0:
+            n_i = min(F, (F + gop - 1) // gop) * mbw * mbh
+            n_p = F * mbw * mbh - n_i
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            alu = n_p * ap['alu_warp_instr_per_macroblock']['P'] + n_i * ap['alu_warp_instr_per_macroblock']['I']
+            bound_ms = alu * ap['cycles_per_alu_warp_instr_per_smsp'] / (sms * 4) / (clk * 1e3)
+            roofline['alu_pipe'] = {'bound_ms_per_step': round(bound_ms, 3), 'achieved_ms_per_step': round(k1_ms, 3), 'frac': round(bound_ms / k1_ms, 4),
+                                    'alu_warp_instr_per_macroblock': ap['alu_warp_instr_per_macroblock'], 'sm_mhz': clk,
+                                    'note': 'ALU-pipe issue time of the K1 launches of a step / their measured time (VECTOR_LEVEL=3 counts)'}
     except Exception:
         pass
 

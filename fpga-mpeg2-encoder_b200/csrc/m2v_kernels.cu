@@ -702,10 +702,12 @@ __device__ __forceinline__ void put_bits(uint32_t *words, unsigned long long pos
 // code for (level v != 0, run) - RTL:2525-2547.  Returns (len<<24 | code) with the sign included.
 __device__ __forceinline__ void ac_code(int v, int run, uint32_t &code, int &len) {
     const int m = abs(v) - 1;
-    const bool tab = (run == 0 && m < 40) || (run == 1 && m < 18) || (run == 2 && m < 5) || (run == 3 && m < 4) ||
-                     (run >= 4 && ((run <= 6 && m < 3) || (run <= 16 && m < 2) || (run <= 31 && m < 1)));
-    if (tab) {
-        const uint32_t e = __ldg(&d_vlc_ac[run * M2V_AC_LEVELS + m]);
+    // The (run, level) pairs the RTL codes from its two tables (RTL:2533-2541: run 0 m<40, run 1 m<18, run 2 m<5, run 3 m<4,
+    // run<=6 m<3, run<=16 m<2, run<=31 m<1) are exactly the populated entries of Table B-14 (tests/test_host_logic.py),
+    // so one bounds check and a zero test of the entry replace the chain of range comparisons.
+    uint32_t e = 0;
+    if (m < M2V_AC_LEVELS && run < 32) e = __ldg(&d_vlc_ac[run * M2V_AC_LEVELS + m]);
+    if (e) {
         code = ((e & 0xFFFF) << 1) | (v < 0);
         len = (int)(e >> 16) + 1;
     } else {

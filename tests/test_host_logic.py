@@ -68,6 +68,19 @@ def test_reciprocal_division_is_exact():
         assert ((n * r) >> np.uint64(32) == n // np.uint64(w)).all(), w
 
 
+def test_ac_table_occupancy_equals_the_rtl_ranges():
+    """K2 decides "table code or escape" by looking the (run, level) pair up in Table B-14 and testing the entry for
+    zero; the RTL decides with range comparisons (RTL:2533-2541).  Same set of pairs."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import gen_tables as G
+    ac = G.build_ac()
+    for run in range(64):
+        for m in range(2047):
+            tab = (run == 0 and m < 40) or (run == 1 and m < 18) or (run == 2 and m < 5) or (run == 3 and m < 4) or \
+                  (run >= 4 and ((run <= 6 and m < 3) or (run <= 16 and m < 2) or (run <= 31 and m < 1)))
+            assert tab == (run < 32 and m < 40 and ac[run][m][1] != 0), (run, m)
+
+
 def test_index_decode_is_exact():
     """K1 turns a drawn macroblock index into (GOP, row, column) with umulhi(n, ceil(2^32/d)), d = macroblocks per row /
     rows per frame (4..128): exact for every n below 2^25 = M2V_K1_MAX_MBS, the per-launch bound the host enforces."""

@@ -86,7 +86,14 @@ def main():
         elif curb is not None:
             curb['rows'].append(r)
     want = kern.replace('ILi', '<').split('<')[0].replace('_Z12', '')
-    blk = next((b for b in blocks if 'k1_mb_encode' in b['name'] and ('true' in b['name'] or '1>' in b['name'])), blocks[0]) if 'k1' in kern else blocks[0]
+    if 'k1' in kern:
+        pf = 'Lb1' in kern or 'Lb' not in kern                   # P-frame instantiation unless the mangled name says <.., false>
+        tag = ('true', '1>') if pf else ('false', '0>')
+        blk = next((b for b in blocks if 'k1_mb_encode' in b['name'] and any(t in b['name'] for t in tag)), blocks[0])
+    else:
+        base = kern.split('I')[0].lstrip('_Z0123456789')
+        tag = '(bool)1' if 'Lb1' in kern else '(bool)0' if 'Lb0' in kern else ''
+        blk = next((b for b in blocks if base in b['name'] and tag in b['name']), blocks[0])
     h = blk['rows'][0]
     ie, ws = h.index('Instructions Executed'), h.index('Warp Stall Sampling (All Samples)')
     rows = [r for r in blk['rows'][1:] if len(r) == len(h)][:len(seq)]
