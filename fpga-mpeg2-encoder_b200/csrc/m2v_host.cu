@@ -437,7 +437,7 @@ extern "C" int m2v_drain(m2v_encoder *e, uint8_t *dst, size_t cap, size_t *n, in
     if (!e || !dst || !n) return M2V_EINVAL;
     size_t avail = (e->outq.size() - e->out_rd) / 32 * 32;
     size_t take = std::min(avail, cap / 32 * 32);
-    memcpy(dst, e->outq.data() + e->out_rd, take);
+    if (take) memcpy(dst, e->outq.data() + e->out_rd, take);
     e->out_rd += take; *n = take;
     const bool fin = e->ended && e->out_rd == e->outq.size();
     if (last) *last = fin && take > 0;

@@ -254,6 +254,78 @@ def test_streaming_full_size_multi_batch(pkg, ob, synth):
     assert got == pkg.finish_stream(pkg.sequence_header(W // 16, H // 16) + b''.join(bodies))
 
 
+def test_randomized_sequences(pkg, ob, synth):
+    """a seeded sweep over sizes, lengths, GOP lengths, parameters, clip classes and stop positions (the reference's
+    testbench exercises exactly one point of this space, TB:23-24,98-99,106)"""
+    rng = np.random.default_rng(20261017)
+    gens = [synth.s1_pan, synth.s2_white, synth.s3_dark, synth.s4_edges]
+    encs = {}
+    for case in range(28):
+        W, H = 16 * int(rng.integers(4, 17)), 16 * int(rng.integers(4, 13))
+        n = int(rng.integers(1, 8))
+        P = int(rng.choice([0, 1, 2, 3, 5, 23, 255]))
+        VL, Q = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+        gen = gens[int(rng.integers(0, 4))]
+        partial = int(rng.integers(1, W * H // 4)) if rng.random() < 0.3 else 0
+        fr = gen(1000 + case, n, W, H)
+        if (VL, Q) not in encs:
+            encs[(VL, Q)] = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=Q)
+        enc = encs[(VL, Q)]                                      # handles are reused across sequences, like the testbench's one instance
+        if rng.random() < 0.5:
+            enc.set_limits(batch_frames=int(rng.integers(1, 6)), chunk_frames=int(rng.integers(1, 6)))
+        else:
+            enc.set_limits(0, 0)
+        got = enc.encode_sequence(fr, P, partial_px4=partial)
+        want = ob.encode(fr, W // 16, H // 16, P, XL=7, YL=7, VL=VL, Q=Q, partial_px4=partial)
+        assert got == want, (case, W, H, n, P, VL, Q, gen.__name__, partial)
+    for e in encs.values():
+        e.close()
+
+
+def test_contract_errors_and_state_machine(pkg, synth):
+    """error behaviour at the boundary: parameters outside README.md:79-84 are rejected, a new sequence cannot start
+    while o_sequence_busy is high (README.md:222), pixels before begin / after stop are refused, a stop while idle is
+    ignored (RTL:1090), and busy falls only when the o_last word has been pulled (RTL:1045-1047, 1095)"""
+    M = pkg.M2VError
+    for bad in (dict(XL=3), dict(XL=8), dict(YL=3), dict(VECTOR_LEVEL=0), dict(VECTOR_LEVEL=4), dict(Q_LEVEL=0), dict(Q_LEVEL=5)):
+        with pytest.raises(M) as ei:
+            pkg.Mpeg2Encoder(**bad)
+        assert ei.value.code == -1                               # M2V_EINVAL
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    fr = synth.s1_pan(1, 2, 64, 64)
+    with pytest.raises(M) as ei:                                 # push before begin
+        enc.push4(fr[0, 0, 0, :4], fr[0, 1, 0, :4], fr[0, 2, 0, :4])
+    assert ei.value.code == -2                                   # M2V_ESTATE
+    enc.sequence_stop()                                          # stop while idle: ignored
+    assert not enc.sequence_busy and enc.pull() is None
+    with pytest.raises(M):
+        enc.begin(4, 4, 256)                                     # i_pframes_count is 8 bit
+    assert enc.begin(2, 99, 1) == (4, 64)                        # clamp to [4, 2^YL] (RTL:985-991)
+    enc.begin(4, 4, 1)                                           # not armed yet (no pixel): begin again is legal
+    assert not enc.sequence_busy
+    enc.push_frames(fr)
+    assert enc.sequence_busy
+    with pytest.raises(M) as ei:
+        enc.begin(4, 4, 1)
+    assert ei.value.code == -2
+    enc.sequence_stop()
+    with pytest.raises(M) as ei:                                 # pixels after the stop, before the stream is pulled
+        enc.push_frames(fr)
+    assert ei.value.code == -2
+    words = []
+    while True:
+        assert enc.sequence_busy                                 # busy until the o_last word is out
+        w = enc.pull()
+        words.append(w[0])
+        if w[1]:
+            break
+    assert not enc.sequence_busy and enc.pull() is None
+    enc2 = pkg.Mpeg2Encoder(XL=6, YL=6)
+    assert b''.join(words) == enc2.encode_sequence(fr, 1)
+    assert enc.encode_sequence(fr, 1) == b''.join(words)          # the handle is reusable after the sequence ended
+    enc.close(); enc2.close()
+
+
 def test_testbench_replay_cli(pkg, ob, synth, tmp_path):
     """csrc/m2venc_tb.cpp = C++ host replaying TB:142-274 through the C-ABI: several videos back to back on one
     instance (TB:150), one frame per push like the testbench's frame loop, and the 4-pixel port (-push4)."""
