@@ -140,10 +140,18 @@ __device__ __forceinline__ void idct_col(const int a[8], int o[8]) {
 // K1
 // ------------------------------------------------------------------------------------------------
 #define K1_WARPS 8
-#define TSTR 72                      // padded tile stride (words) of the transform scratch
+// Shared-memory strides chosen against bank conflicts (the I-frame kernel is bound by shared-memory wavefronts: ncu
+// showed l1tex at 97 % with 38 % of the wavefronts caused by conflicts):
+#define TROW 12                      // words per row of a transform scratch tile: 128-bit row accesses of 8 lanes hit 8 distinct bank quads
+#define TSTR 104                     // words per scratch tile (8 rows x 12 + 8): the 4 tile groups' column accesses fall in distinct bank octets
+#define RSTR 72                      // halfwords per level tile (64 + 8): the zig-zag scatter of the 4 tile groups is spread over the banks
+#define PSTR 72                      // bytes per prediction tile (64 + 8): byte accesses of the 4 tile groups do not collide
 // One pipeline stage = everything TMA brings in for one macroblock.  Every member is a dense TMA box
-// and starts on a 128-byte boundary.
-struct __align__(128) StageSmem {
+// and starts on a 128-byte boundary.  The I-frame instantiation needs no windows: its warps take 4.3 KB instead
+// of 8.3 KB of shared memory, which (with 64 registers) lets a fourth CTA live on every SM - the I-frame kernel is
+// bound by the latency of its shared-memory transposes, not by a pipe, so it is the resident warps that count.
+template <bool PF> struct StageSmemT;
+template <> struct __align__(128) StageSmemT<true> {
     uint32_t curY[16][4];            // current luma block, 16 rows x 16 B      } one box 16x16x3 over the planes
     uint32_t curU[16][4];            // current 4:4:4 U block                   } Y,U,V of the input frame
     uint32_t curV[16][4];            //                 V                        }
@@ -152,12 +160,23 @@ struct __align__(128) StageSmem {
     uint32_t winC[2][16][8];         // chroma windows: rows 8by-4..8by+11, 32 bytes from (8bx-8)&~15     (2 boxes 32x16)
     uint32_t winY[32][12];           // luma window: rows Y0-(R+1)..Y0+16+R, bytes X0-16..X0+31           (box 48 x (18+2R))
 };
-struct __align__(128) WarpSmem {
-    StageSmem st[2];                 // double buffer: TMA fills st[k^1] while st[k] is being encoded
+template <> struct __align__(128) StageSmemT<false> {
+    uint32_t curY[16][4], curU[16][4], curV[16][4];
+};
+template <bool PF> struct WarpSmemT;
+template <> struct __align__(128) WarpSmemT<true> {
+    StageSmemT<true> st[2];          // double buffer: TMA fills st[k^1] while st[k] is being encoded
     uint32_t curC[2][8][2];          // current 4:2:0 chroma blocks
-    int16_t res[8][64];              // residual, later the zig-zag levels; tiles 6,7 are all-zero dummies that keep lanes
-    uint8_t pred[8][64];             // prediction, later the reconstruction          16..31 busy in the chroma round
-};                                   // 8320 bytes; the two mbarriers of each warp live after the warps' areas
+    int16_t res[8][RSTR];            // residual, later the zig-zag levels; tiles 6,7 are all-zero dummies that keep lanes
+    uint8_t pred[8][PSTR];           // prediction, later the reconstruction          16..31 busy in the chroma round
+};                                   // 8576 bytes; the two mbarriers of each warp live after the warps' areas
+template <> struct __align__(128) WarpSmemT<false> {
+    StageSmemT<false> st[2];
+    uint32_t scratch[4 * TSTR];      // transform scratch (the P-frame kernel aliases it onto the dead windows)
+    uint32_t curC[2][8][2];
+    int16_t res[8][RSTR];
+    uint8_t pred[8][PSTR];
+};                                   // 5120 bytes
 // the transform scratch (4 tile slots x TSTR words) aliases winC+winY of the stage being encoded:
 // the windows are dead once the prediction has been formed.
 static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratch must fit in the window area");
@@ -198,13 +217,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm,
 // (With a static stride the warps of an SM sub-partition finish far apart - the scheduler favours some of them -
 // and the tail runs at a fraction of the occupancy: ncu showed 4.5 of 6 resident warps active on average.)
 template <int VL, bool PFRAME>
-__global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
+__global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1Args p, const __grid_constant__ CUtensorMap tm_in,
                                                                const __grid_constant__ CUtensorMap tm_refY,
                                                                const __grid_constant__ CUtensorMap tm_refC) {
     constexpr int R = 2 * VL;
     constexpr int WROWS = 18 + 2 * R;
     constexpr uint32_t TX_BYTES = 3 * 256 + (PFRAME ? 2 * 512 + 48 * WROWS : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];     // keeps the .shared address space: LDS/STS, not generic LD/ST
+    typedef WarpSmemT<PFRAME> WarpSmem;
+    typedef StageSmemT<PFRAME> StageSmem;
     QEntry *const qt = reinterpret_cast<QEntry *>(smem_raw + sizeof(WarpSmem) * K1_WARPS);   // 64 entries after the warps' areas
     unsigned long long *const bars = reinterpret_cast<unsigned long long *>(qt + 64) + 2 * (threadIdx.x >> 5);   // one mbarrier per stage
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         const uint32_t bar = smem_u32(&bars[stg]);
         mbar_expect_tx(bar, TX_BYTES);
         tma_load_4d(smem_u32(S.curY), &tm_in, m.bx * 16, m.by * 16, 0, n, bar);       // one 16x16x3 box: curY, curU, curV
-        if (PFRAME) {
+        if constexpr (PFRAME) {
             // out-of-frame parts of a box are zero-filled by TMA; they only ever feed candidates the border
             // rule disables (RTL:1642-1645, 1757-1760).  (RTL:1350-1425, 1613-1629 fetch the same windows.)
             const int cx0 = (m.bx * 8 - 8) & ~15;
@@ -240,8 +261,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);   // one 32x16x2 box: U and V windows
         }
     };
-    reinterpret_cast<uint2 *>(&s.res[6][0])[lane] = make_uint2(0, 0);          // dummy tiles: zero residual, zero prediction
-    reinterpret_cast<uint32_t *>(&s.pred[6][0])[lane] = 0;
+    for (int i = lane; i < 2 * RSTR / 2; i += 32) reinterpret_cast<uint32_t *>(&s.res[6][0])[i] = 0;    // dummy tiles: zero residual,
+    for (int i = lane; i < 2 * PSTR / 4; i += 32) reinterpret_cast<uint32_t *>(&s.pred[6][0])[i] = 0;   // zero prediction
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
     // lane 0 draws the next index; the value is only looked at one macroblock later
     auto draw = [&]() { unsigned v = 0; if (lane == 0) v = nwarps + atomicAdd(p.ctr, 1u); return v; };
@@ -269,7 +290,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     const long n = (long)g * (p.P + 1) + p.t;               // frame index inside the batch
     const int Y0 = by * 16, X0 = bx * 16;
     StageSmem &S = s.st[stg];
-    int32_t *const tmp = reinterpret_cast<int32_t *>(&S.winC[0][0][0]);
+    int32_t *tmp;
+    if constexpr (PFRAME) tmp = reinterpret_cast<int32_t *>(&S.winC[0][0][0]); else tmp = reinterpret_cast<int32_t *>(s.scratch);
     mbar_wait(smem_u32(&bars[stg]), (phase >> stg) & 1u);
     phase ^= 1u << stg;
 
@@ -286,7 +308,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
     __syncwarp();
 
     int inter = 0, mvx = 0, mvy = 0;
-    if (PFRAME) {
+    if constexpr (PFRAME) {
         // ---- full-pel search (RTL:1634-1715).  lane = dxi + 16*half: candidate column dx = dxi-R,
         //      half = which 8 bytes of every 16-byte row.  Each lane keeps 2R+1 accumulators (one
         //      per dy) and walks the window rows once.
@@ -474,13 +496,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
             x[4] = (int16_t)(rv.z & 0xFFFF); x[5] = (int32_t)rv.z >> 16; x[6] = (int16_t)(rv.w & 0xFFFF); x[7] = (int32_t)rv.w >> 16;
             fdct8(x, o);
 #pragma unroll
-            for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
+            for (int j = 0; j < 8; j++) tt[v * TROW + j] = o[j];
         }
         __syncwarp();
         bool nzl = false, maybe = true;
         {                                                        // columns: B = DCTM * A (RTL:2054-2057)
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
+            for (int k = 0; k < 8; k++) x[k] = tt[k * TROW + v];
             fdct8(x, o);
             if (inter) {
                 // Inter levels are (|C|+2)>>(4+Q) with C = (B+2048)>>12: zero whenever |B| < 4096*(2^(4+Q)-2) - 2048.
@@ -555,20 +577,20 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
                     for (int i = 0; i < 8; i++) o[i] = 0;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) tt[i * 8 + v] = o[i];
+                for (int i = 0; i < 8; i++) tt[i * TROW + v] = o[i];
             }
             __syncwarp();
             if (inv) {                                           // inverse rows (in place)
 #pragma unroll
-                for (int j = 0; j < 8; j++) x[j] = tt[v * 8 + j];
+                for (int j = 0; j < 8; j++) x[j] = tt[v * TROW + j];
                 idct_row(x, o);
 #pragma unroll
-                for (int j = 0; j < 8; j++) tt[v * 8 + j] = o[j];
+                for (int j = 0; j < 8; j++) tt[v * TROW + j] = o[j];
             }
             __syncwarp();
             if (inv) {                                           // inverse columns, add prediction, clip (RTL:2352)
 #pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = tt[k * 8 + v];
+                for (int k = 0; k < 8; k++) x[k] = tt[k * TROW + v];
                 idct_col(x, o);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -593,11 +615,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_mb_encode(K1Args p, const
         }
         const size_t mbi = (size_t)n * p.nmb + mb;
         uint2 *dst = (uint2 *)(p.coefs + mbi * 384);
-        const uint2 *src = (const uint2 *)&s.res[0][0];
         // a tile whose cbp bit is clear holds no level and K2 never reads it (RTL:2799, 2804, 2828): not written
 #pragma unroll
         for (int k = 0; k < 3; k++)
-            if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = src[lane + 32 * k];
+            if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = *(const uint2 *)&s.res[2 * k + (lane >> 4)][(lane & 15) * 4];
         if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
     }
     __syncwarp();
@@ -649,21 +670,20 @@ bool m2v_make_tmaps(M2VBatch &b) {
     return true;
 }
 
-static int k1_grid_cap = 0;
 template <int VL, bool PF>
 static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream_t st) {
-    const size_t smem = sizeof(WarpSmem) * K1_WARPS + 64 * sizeof(QEntry) + 16 * K1_WARPS;
-    static bool attr_done = false;
-    if (!attr_done) {
+    const size_t smem = sizeof(WarpSmemT<PF>) * K1_WARPS + 64 * sizeof(QEntry) + 16 * K1_WARPS;
+    static int grid_cap = 0;                                      // persistent grid = every CTA the device can hold at once
+    if (!grid_cap) {
         cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    if (!k1_grid_cap) {
-        int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        k1_grid_cap = sms * 3;                                     // 3 resident CTAs of 8 warps per SM (shared-memory bound; 4x7 warps at 72 registers measured slower)
+        int dev = 0, sms = 0, per_sm = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // P-frame kernel: 3 CTAs of 8 warps per SM (80 registers, 8.3 KB of shared memory per warp; 4x7 warps at 72
+        // registers measured slower); I-frame kernel: 4 CTAs (64 registers, 4.3 KB per warp)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_mb_encode<VL, PF>, K1_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = PF ? 3 : 4;
+        grid_cap = sms * per_sm;
     }
     unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
-    if (grid > (unsigned)k1_grid_cap) grid = k1_grid_cap;
+    if (grid > (unsigned)grid_cap) grid = grid_cap;
     k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, smem, st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
 }
 
