@@ -62,8 +62,13 @@ __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
 __device__ __forceinline__ uint32_t exlo(uint32_t v) { return __byte_perm(v, 0, 0x4140); }   // bytes 0,1 -> halfwords
 __device__ __forceinline__ uint32_t exhi(uint32_t v) { return __byte_perm(v, 0, 0x4342); }   // bytes 2,3 -> halfwords
 __device__ __forceinline__ uint32_t pack4(uint32_t h0, uint32_t h1) { return __byte_perm(h0, h1, 0x6420); }
-// mean4 on packed halfwords: (s + 1) >> 2 with the RTL's +1 rounding (RTL:760-767)
-__device__ __forceinline__ uint32_t m4h(uint32_t s) { return ((s + 0x00010001u) >> 2) & 0x00FF00FFu; }
+// mean4 on packed halfwords: (s + 1) >> 2 with the RTL's +1 rounding (RTL:760-767).  A sum of four bytes plus one is below
+// 1024, so after the shift each result sits in byte 0 / byte 2 of the word with nothing above it; bytes 1 and 3 hold shifted-in
+// garbage that pack4 never selects - no mask needed.
+__device__ __forceinline__ uint32_t m4h(uint32_t s) { return (s + 0x00010001u) >> 2; }
+// mean2 of four byte pairs (RTL:750-757): (a + b + 1) >> 1 == (a | b) - ((a ^ b) >> 1) per byte; the subtraction never borrows
+// across bytes.  One LOP3 less than the compiler's expansion of __vavgu4.
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
 
 // RTL:804-840
 __device__ __forceinline__ int find_min10(const int v[10]) {
@@ -300,10 +305,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     {
         const int comp = lane >> 4, r = lane & 15;
         uint4 v = *(const uint4 *)(comp ? S.curV[r] : S.curU[r]);
-        uint32_t h0 = __vavgu4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
-        uint32_t h1 = __vavgu4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
+        uint32_t h0 = avg4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
+        uint32_t h1 = avg4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
         uint32_t g0 = __shfl_xor_sync(FULL, h0, 1), g1 = __shfl_xor_sync(FULL, h1, 1);
-        if (!(r & 1)) { s.curC[comp][r >> 1][0] = __vavgu4(g0, h0); s.curC[comp][r >> 1][1] = __vavgu4(g1, h1); }
+        if (!(r & 1)) { s.curC[comp][r >> 1][0] = avg4(g0, h0); s.curC[comp][r >> 1][1] = avg4(g1, h1); }
     }
     __syncwarp();
 
@@ -379,10 +384,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 cand[4][k] = zz[1][k];                                            // f_Y_hlf even,even
-                cand[3][k] = __vavgu4(zm[1][k], zz[1][k]);                        // mean2 left   (RTL:1749)
-                cand[5][k] = __vavgu4(zz[1][k], zp[1][k]);                        // mean2 right
-                cand[1][k] = __vavgu4(zz[0][k], zz[1][k]);                        // mean2 up     (RTL:1750)
-                cand[7][k] = __vavgu4(zz[1][k], zz[2][k]);                        // mean2 down
+                cand[3][k] = avg4(zm[1][k], zz[1][k]);                        // mean2 left   (RTL:1749)
+                cand[5][k] = avg4(zz[1][k], zp[1][k]);                        // mean2 right
+                cand[1][k] = avg4(zz[0][k], zz[1][k]);                        // mean2 up     (RTL:1750)
+                cand[7][k] = avg4(zz[1][k], zz[2][k]);                        // mean2 down
                 // diagonals: mean4 with +1 rounding (RTL:1751, 764) on packed halfwords
                 uint32_t pm[3][2], pp[3][2];                                      // pair sums (x-1,x) and (x,x+1), per row
 #pragma unroll
@@ -391,10 +396,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                     pm[rr][0] = exlo(zm[rr][k]) + zl; pm[rr][1] = exhi(zm[rr][k]) + zh;
                     pp[rr][0] = exlo(zp[rr][k]) + zl; pp[rr][1] = exhi(zp[rr][k]) + zh;
                 }
-                cand[0][k] = pack4(m4h(pm[0][0] + pm[1][0]), m4h(pm[0][1] + pm[1][1]));
-                cand[2][k] = pack4(m4h(pp[0][0] + pp[1][0]), m4h(pp[0][1] + pp[1][1]));
-                cand[6][k] = pack4(m4h(pm[1][0] + pm[2][0]), m4h(pm[1][1] + pm[2][1]));
-                cand[8][k] = pack4(m4h(pp[1][0] + pp[2][0]), m4h(pp[1][1] + pp[2][1]));
+                // every diagonal contains the middle row: its pair sums carry the +1 of the rounding for all four
+                pm[1][0] += 0x00010001u; pm[1][1] += 0x00010001u; pp[1][0] += 0x00010001u; pp[1][1] += 0x00010001u;
+                cand[0][k] = pack4((pm[0][0] + pm[1][0]) >> 2, (pm[0][1] + pm[1][1]) >> 2);
+                cand[2][k] = pack4((pp[0][0] + pp[1][0]) >> 2, (pp[0][1] + pp[1][1]) >> 2);
+                cand[6][k] = pack4((pm[1][0] + pm[2][0]) >> 2, (pm[1][1] + pm[2][1]) >> 2);
+                cand[8][k] = pack4((pp[1][0] + pp[2][0]) >> 2, (pp[1][1] + pp[2][1]) >> 2);
             }
         }
         int key[10];
@@ -453,8 +460,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                 if (oy && ox) {
                     uint32_t lo = exlo(a0) + exlo(a1) + exlo(b0) + exlo(b1), hi = exhi(a0) + exhi(a1) + exhi(b0) + exhi(b1);
                     pc = pack4(m4h(lo), m4h(hi));
-                } else if (ox) pc = __vavgu4(a0, a1);
-                else if (oy) pc = __vavgu4(a0, b0);
+                } else if (ox) pc = avg4(a0, a1);
+                else if (oy) pc = avg4(a0, b0);
                 else pc = a0;
             }
             *(uint32_t *)&s.pred[4 + comp][cyy * 8 + ch * 4] = pc;

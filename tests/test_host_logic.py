@@ -81,6 +81,32 @@ def test_ac_table_occupancy_equals_the_rtl_ranges():
             assert tab == (run < 32 and m < 40 and ac[run][m][1] != 0), (run, m)
 
 
+def test_byte_simd_identities():
+    """the packed-byte forms K1 uses for the RTL's mean2 (RTL:750-757) and mean4 (RTL:760-767), replayed in numpy:
+    avg4(a,b) = (a|b) - (((a^b) & 0xFEFEFEFE) >> 1) per 32-bit word; mean4 on halfword pair sums, +1 folded into one
+    addend, shifted right by 2 WITHOUT a mask, bytes 0 and 2 picked by the byte permute"""
+    rng = np.random.default_rng(3)
+    edge = np.array([0, 1, 2, 127, 128, 254, 255], dtype=np.uint8)
+    def words(n):
+        b = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+        b[: 7 * 7] = np.array([[x, y, 255 - x, y] for x in edge for y in edge], dtype=np.uint8)
+        return b
+    a, b = words(200000), words(200000)[::-1].copy()
+    wa, wb = a.view('<u4')[:, 0].astype(np.uint64), b.view('<u4')[:, 0].astype(np.uint64)
+    got = ((wa | wb) - (((wa ^ wb) & np.uint64(0xFEFEFEFE)) >> np.uint64(1))) & np.uint64(0xFFFFFFFF)
+    want = ((a.astype(np.uint16) + b + 1) >> 1).astype(np.uint8)
+    assert (got.astype('<u4').view(np.uint8).reshape(-1, 4) == want).all()
+    # mean4: four byte planes p,q (row r) and t,u (row r+1); halfword sums of bytes (0,1) and (2,3) as exlo/exhi build them
+    p, q, t, u = words(100000), words(100000)[::-1].copy(), words(100000), words(100000)[::-1].copy()
+    ex = lambda v, i, j: v[:, i].astype(np.uint64) | (v[:, j].astype(np.uint64) << np.uint64(16))
+    for (i, j) in ((0, 1), (2, 3)):
+        s_mid = ex(p, i, j) + ex(q, i, j) + np.uint64(0x00010001)          # the middle row's pair sum carries the +1
+        s = ((s_mid + ex(t, i, j) + ex(u, i, j)) >> np.uint64(2)) & np.uint64(0xFFFFFFFF)
+        b0, b2 = (s & np.uint64(0xFF)).astype(np.uint8), ((s >> np.uint64(16)) & np.uint64(0xFF)).astype(np.uint8)
+        w = lambda k: ((p[:, k].astype(np.uint16) + q[:, k] + t[:, k] + u[:, k] + 1) >> 2).astype(np.uint8)
+        assert (b0 == w(i)).all() and (b2 == w(j)).all()
+
+
 def test_index_decode_is_exact():
     """K1 turns a drawn macroblock index into (GOP, row, column) with umulhi(n, ceil(2^32/d)), d = macroblocks per row /
     rows per frame (4..128): exact for every n below 2^25 = M2V_K1_MAX_MBS, the per-launch bound the host enforces."""
