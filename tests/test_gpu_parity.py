@@ -326,6 +326,21 @@ def test_contract_errors_and_state_machine(pkg, synth):
     enc.close(); enc2.close()
 
 
+def test_long_stream_single_drain(pkg, ob, synth):
+    """white noise at Q_LEVEL=1 codes > 1 byte per pixel: a stream of several MB pulled by ONE m2v_drain call (the
+    multi-threaded queue -> caller copy) equals the oracle's"""
+    W, H, n = 640, 480, 12
+    fr = synth.s2_white(5, n, W, H)
+    enc = pkg.Mpeg2Encoder(XL=6, YL=5, VECTOR_LEVEL=1, Q_LEVEL=1)
+    enc.begin(W // 16, H // 16, 1)
+    enc.push_frames(fr); enc.sequence_stop()
+    buf = np.empty(64 << 20, np.uint8)
+    k, last = enc.drain_into(buf)
+    assert last and k > (4 << 20)
+    assert buf[:k].tobytes() == ob.encode(fr, W // 16, H // 16, 1, XL=6, YL=5, VL=1, Q=1)
+    enc.close()
+
+
 def test_testbench_replay_cli(pkg, ob, synth, tmp_path):
     """csrc/m2venc_tb.cpp = C++ host replaying TB:142-274 through the C-ABI: several videos back to back on one
     instance (TB:150), one frame per push like the testbench's frame loop, and the 4-pixel port (-push4)."""
