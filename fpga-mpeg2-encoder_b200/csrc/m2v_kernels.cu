@@ -3,7 +3,8 @@
 //   K1 mb_encode : one warp per macroblock.  4:4:4->4:2:0 chroma subsample, full-search SAD motion
 //                  estimation, half-pel refinement, intra/inter decision, prediction, 6x 8x8 integer
 //                  DCT, quantise, zig-zag, dequantise, Chen-Wang IDCT, reconstruction.
-//   K1 is launched as persistent warps fed by TMA (cp.async.bulk.tensor + mbarrier, double buffered).
+//   K1 is launched as persistent warps fed by TMA (cp.async.bulk.tensor + mbarrier, double buffered) that draw
+//   their macroblocks from an atomic work counter.
 //   K2 vlc       : one thread per macroblock (lanes = consecutive macroblocks of a slice).  run/level +
 //                  VLC over the sparse levels; count pass (bit length per macroblock) and write pass.
 //   K3 scans     : warp inclusive scans over the per-macroblock bit lengths -> offsets in slice, slice
@@ -490,6 +491,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     //      vector = lane&7); round 1: chroma tiles on lanes 0..15 while lanes 16..31 run the same code on two
     //      all-zero dummy tiles (no predicate, no divergence, warp syncs with the constant full mask - a run-time
     //      mask makes the compiler guard every sync with MATCH/REDUX/VOTE).  (RTL:2029-2077, 2128-2356, 2452-2467)
+    // (Measured and rejected: unrolling the two rounds - the kernel no longer fits the instruction cache and slows down;
+    //  predicating lanes 16..31 off in the chroma round, or syncing only the lower half-warp with __syncwarp(0xFFFF) held in a
+    //  run-time mask - the compiler guards every such sync with MATCH/REDUX/VOTE.)
     int cbp = 0;
     const int Q = p.Q;
 #pragma unroll 1
@@ -685,7 +689,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
         cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         // P-frame kernel: 3 CTAs of 8 warps per SM (80 registers, 8.3 KB of shared memory per warp; 4x7 warps at 72
-        // registers measured slower); I-frame kernel: 4 CTAs (64 registers, 4.3 KB per warp)
+        // registers measured slower); I-frame kernel: 4 CTAs (64 registers, 5.1 KB per warp)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_mb_encode<VL, PF>, K1_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = PF ? 3 : 4;
         grid_cap = sms * per_sm;
     }
