@@ -341,6 +341,31 @@ def test_long_stream_single_drain(pkg, ob, synth):
     enc.close()
 
 
+def test_config1_testbench_clips(pkg):
+    """BASELINE.json config 1 through the CUDA path: the testbench's three clips back to back on one instance with its default
+    parameters (TB:23-24, 98-99, 106, 150).  The expected lengths and hashes were written by the reference RTL itself
+    (tests/golden/clips_sha256.json); 1440x704 must come out at the 775 456 bytes the reference publishes (README.md:748).
+    The clips are unpacked by `make -C oracle` into the git-ignored oracle/_ref/data and only exist where they travelled."""
+    import hashlib, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = os.path.join(root, 'oracle', '_ref', 'data')
+    meta = json.load(open(os.path.join(GOLD, 'clips_sha256.json')))
+    if not all(os.path.exists(os.path.join(data, n + '.yuv')) for n in meta):
+        pytest.skip('testbench clips not on this box')
+    enc = pkg.Mpeg2Encoder(XL=7, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2)
+    for name in ('288x208', '640x320', '1440x704'):
+        W, H = (int(x) for x in name.split('x'))
+        raw = np.fromfile(os.path.join(data, name + '.yuv'), dtype=np.uint8)
+        assert hashlib.sha256(raw.tobytes()).hexdigest() == meta[name]['input_sha256']
+        fr = raw.reshape(-1, 3, H, W)
+        assert fr.shape[0] == meta[name]['frames']
+        got = enc.encode_sequence(fr, 23)
+        assert len(got) == meta[name]['length'], name
+        assert hashlib.sha256(got).hexdigest() == meta[name]['sha256'], name
+    assert meta['1440x704']['length'] == 775456
+    enc.close()
+
+
 def test_testbench_replay_cli(pkg, ob, synth, tmp_path):
     """csrc/m2venc_tb.cpp = C++ host replaying TB:142-274 through the C-ABI: several videos back to back on one
     instance (TB:150), one frame per push like the testbench's frame loop, and the 4-pixel port (-push4)."""
