@@ -188,3 +188,20 @@ def test_tables_generator_is_current():
     assert open(os.path.join(ROOT, 'oracle', 'm2v_tables.h')).read() == G.emit('', 'M2V_ORACLE_TABLES_H', 'Oracle copy (test infrastructure).')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_tables_vs_rtl.py')], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints exactly one JSON line on stdout with
+    the contract's keys; here on the smallest configuration so that it takes seconds"""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', '2', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'Mpixel/s' and d['higher_is_better'] is True and d['value'] > 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['sample']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and d['vs_baseline'] is None and d['dtype'] == 'u8'
