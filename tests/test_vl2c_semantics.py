@@ -7,6 +7,10 @@ assignment), not by running any simulator:
   comb.v  context-determined widths (carry kept or lost), zero- vs sign-extension by the propagated type, signed x
           unsigned products, >>> on signed / unsigned operands, signed / unsigned comparisons, unsized literals widening
           the context to 32 bits, truncating signed division and modulo, concatenation, replication, reductions, +: selects
+  wide.v  vectors wider than 64 bits as the RTL's bit packer uses them (RTL:2879-2994): wide concatenations, OR, a variable
+          left shift, an indexed part select, a concatenation on the left-hand side, wide equality, byte reversal (relational operators on wide vectors are
+          outside the translator's subset - it refuses them - and the RTL does not use them).
+          Expected values: Python integers applying the definitions (concatenation = shift and or, truncation = mod 2^n).
   seq.v   non-blocking swap, blocking temporaries inside a clocked block, counter wrap, concatenation on the left-hand
           side, an array with negative bounds read before written, a blocking for-loop accumulation, case, functions with
           sized arguments / local regs / signed clipping, asynchronous reset
@@ -104,3 +108,35 @@ int main() {
     assert len(rows) == len(want)
     for k, (g, w) in enumerate(zip(rows, want)):
         assert all(b is None or a == b for a, b in zip(g, w)), (k, g, w)
+
+
+def test_wide_vectors(tmp_path):
+    harness = r'''
+static void pw(const char *n, const Big &v, int bits) { printf("%s ", n); for (int i = bits - 4; i >= 0; i -= 4) printf("%llx", (unsigned long long)v.slice(i, 4)); printf("\n"); }
+int main() {
+    Sim s; s.init();
+    s.v_rstn = 1; s.clock(); s.v_rstn = 0; s.clock(); s.v_rstn = 1;
+    for (int k = 1; k <= 27; k++) { s.v_din = (unsigned)(k * 7 + 3) & 255; s.clock(); }
+    s.v_x64 = 0xDEADBEEF00C0FFEEull; s.v_sh = 140; s.v_sel = 19; s.comb();
+    pw("acc", s.v_acc, 200); pw("w", s.v_w, 256); pw("hi128", s.v_hi128, 128); pw("lo72", s.v_lo72, 72); pw("le", s.v_le, 256);
+    printf("wbyte %llx\neq %llu\n", (unsigned long long)s.v_wbyte, (unsigned long long)s.v_eq);
+    s.v_sh = 300; s.comb();                                   // shifted entirely out of the 256-bit context
+    pw("w300", s.v_w, 256);
+    return 0;
+}
+'''
+    out = dict(l.split() for l in _run(tmp_path, 'wide', [], harness).splitlines())
+    acc = prev = 0
+    for k in range(1, 28):                                        # 27 bytes through a 25-byte register
+        prev = acc
+        acc = ((acc << 8) | ((k * 7 + 3) & 255)) & ((1 << 200) - 1)
+    x = 0xDEADBEEF00C0FFEE
+    w = ((acc << 56) | (x << 140)) & ((1 << 256) - 1)
+    le = int.from_bytes(w.to_bytes(32, 'big')[::-1], 'big')
+    assert int(out['acc'], 16) == acc
+    assert int(out['w'], 16) == w
+    assert int(out['hi128'], 16) == prev >> 72 and int(out['lo72'], 16) == prev & ((1 << 72) - 1)   # the OLD acc
+    assert int(out['wbyte'], 16) == (w >> (8 * 19)) & 255
+    assert int(out['eq']) == int(prev == acc) == 0
+    assert int(out['le'], 16) == le
+    assert int(out['w300'], 16) == (acc << 56) & ((1 << 256) - 1)
