@@ -28,7 +28,9 @@ ABI_SYMBOLS = [
     'm2v_create', 'm2v_destroy', 'm2v_last_error', 'm2v_begin', 'm2v_push4', 'm2v_push_frames', 'm2v_stop',
     'm2v_busy', 'm2v_pull', 'm2v_drain', 'm2v_encode_gops_device', 'm2v_encode_gops_host',
     'm2v_sequence_header', 'm2v_finish_stream', 'm2v_debug_copy', 'm2v_launch_count', 'm2v_kernel_ms',
-    'm2v_set_timing', 'm2v_set_limits',
+    'm2v_set_timing', 'm2v_set_limits', 'm2v_set_body_reserve', 'm2v_create_multi', 'm2v_device_count',
+    'm2v_gops_submit', 'm2v_gops_size', 'm2v_gops_fetch', 'm2v_gops_wait', 'm2v_gops_body',
+    'm2v_alloc_host', 'm2v_free_host', 'm2v_register_host', 'm2v_unregister_host',
 ]
 
 
@@ -74,6 +76,18 @@ def lib():
         L.m2v_kernel_ms.argtypes = [vp, vp]
         L.m2v_set_timing.argtypes = [vp, ip]
         L.m2v_set_limits.argtypes = [vp, C.c_long, C.c_long]
+        L.m2v_set_body_reserve.argtypes = [vp, C.c_long]
+        L.m2v_create_multi.argtypes = [ip, ip, ip, ip, ip, C.POINTER(vp)]
+        L.m2v_device_count.argtypes = [vp]
+        L.m2v_gops_submit.argtypes = [vp, ip, ip, ip, vp, C.c_long, C.c_long, ip]
+        L.m2v_gops_size.argtypes = [vp, ip, C.POINTER(sz)]
+        L.m2v_gops_fetch.argtypes = [vp, ip, vp, sz]
+        L.m2v_gops_wait.argtypes = [vp, ip]
+        L.m2v_gops_body.argtypes = [vp, ip, C.POINTER(vp)]
+        L.m2v_alloc_host.argtypes = [sz]; L.m2v_alloc_host.restype = vp
+        L.m2v_free_host.argtypes = [vp]; L.m2v_free_host.restype = None
+        L.m2v_register_host.argtypes = [vp, sz]
+        L.m2v_unregister_host.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -103,13 +117,35 @@ def finish_stream(data):
     return bytes(buf[:tot.value])
 
 
-class Mpeg2Encoder:
-    """One instance of the reference module: parameters are fixed at construction (RTL:11-14)."""
+class PinnedArray:
+    """uint8 numpy view over pinned host memory from m2v_alloc_host (frames to push, or a sink for m2v_drain)."""
 
-    def __init__(self, XL=6, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2):
+    def __init__(self, nbytes):
+        self.ptr = lib().m2v_alloc_host(nbytes)
+        if not self.ptr:
+            raise M2VError(M2V_ENOMEM, 'm2v_alloc_host(%d)' % nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if getattr(self, 'ptr', None):
+            self.array = None
+            lib().m2v_free_host(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+
+class Mpeg2Encoder:
+    """One instance of the reference module: parameters are fixed at construction (RTL:11-14).  ndev > 1 spreads the
+    instance over devices 0..ndev-1 of this process (m2v_create_multi); the stream is the same."""
+
+    def __init__(self, XL=6, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2, ndev=1):
         self._h = C.c_void_p()
         self.XL, self.YL, self.VECTOR_LEVEL, self.Q_LEVEL = XL, YL, VECTOR_LEVEL, Q_LEVEL
-        rc = lib().m2v_create(XL, YL, VECTOR_LEVEL, Q_LEVEL, C.byref(self._h))
+        if ndev == 1:
+            rc = lib().m2v_create(XL, YL, VECTOR_LEVEL, Q_LEVEL, C.byref(self._h))
+        else:
+            rc = lib().m2v_create_multi(ndev, XL, YL, VECTOR_LEVEL, Q_LEVEL, C.byref(self._h))
         if rc:
             self._h = None
             raise M2VError(rc, 'm2v_create (a B200 / sm_100 device is required; there is no CPU fallback)')
@@ -214,6 +250,34 @@ class Mpeg2Encoder:
         self._ck(lib().m2v_encode_gops_host(self._h, mbw, mbh, pframes_count, C.c_void_p(dev_ptr), nframes, n0,
                                             out.ctypes.data, out.nbytes, C.byref(n)))
         return n.value
+
+    # ---- asynchronous chunks (two slots): submit -> size (known after the scans) -> fetch (device->host) -> wait ----
+    def gops_submit(self, dev_ptr, nframes, n0, mbw, mbh, pframes_count, slot):
+        self._ck(lib().m2v_gops_submit(self._h, mbw, mbh, pframes_count, C.c_void_p(dev_ptr), nframes, n0, slot))
+
+    def gops_size(self, slot):
+        n = C.c_size_t(0)
+        self._ck(lib().m2v_gops_size(self._h, slot, C.byref(n)))
+        return n.value
+
+    def gops_fetch(self, slot, host_ptr, nbytes):
+        self._ck(lib().m2v_gops_fetch(self._h, slot, C.c_void_p(host_ptr), nbytes))
+
+    def gops_wait(self, slot):
+        self._ck(lib().m2v_gops_wait(self._h, slot))
+
+    def gops_body(self, slot):
+        d = C.c_void_p()
+        self._ck(lib().m2v_gops_body(self._h, slot, C.byref(d)))
+        return d.value
+
+    @property
+    def device_count(self):
+        return lib().m2v_device_count(self._h)
+
+    def set_body_reserve(self, bytes_per_macroblock):
+        """test knob (m2v_set_body_reserve): body bytes reserved per macroblock; a tiny value forces the regrow-and-rerun path"""
+        self._ck(lib().m2v_set_body_reserve(self._h, int(bytes_per_macroblock)))
 
     def debug_copy(self, count):
         info = np.zeros(count, np.uint32); coefs = np.zeros((count, 6, 64), np.int16)

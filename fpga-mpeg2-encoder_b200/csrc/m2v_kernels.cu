@@ -37,7 +37,7 @@ cudaError_t m2v_upload_tables(int) {
     if ((e = cudaMemcpyToSymbol(c_vlc_dcy, M2V_VLC_DC_Y, sizeof(M2V_VLC_DC_Y)))) return e;
     if ((e = cudaMemcpyToSymbol(c_vlc_dcc, M2V_VLC_DC_C, sizeof(M2V_VLC_DC_C)))) return e;
     if ((e = cudaMemcpyToSymbol(d_vlc_ac, M2V_VLC_AC, sizeof(M2V_VLC_AC)))) return e;
-    static QEntry h[4][64];
+    QEntry h[4][64];                                        // per call: several devices / threads may upload concurrently
     for (int q = 1; q <= 4; q++)
         for (int i = 0; i < 64; i++) {
             uint32_t w = M2V_INTRA_Q[i];
@@ -67,6 +67,11 @@ __device__ __forceinline__ uint32_t pack4(uint32_t h0, uint32_t h1) { return __b
 // 1024, so after the shift each result sits in byte 0 / byte 2 of the word with nothing above it; bytes 1 and 3 hold shifted-in
 // garbage that pack4 never selects - no mask needed.
 __device__ __forceinline__ uint32_t m4h(uint32_t s) { return (s + 0x00010001u) >> 2; }
+// Residuals are staged as halfwords biased by +256 (always positive: the packed subtraction needs no per-halfword borrow
+// handling - one IADD3 per two pixels).  The forward transform is linear and every row of the RTL's matrix except the first sums
+// to zero, so the bias only shifts the first output of the row pass, by 64*8*256, which is subtracted there as an immediate.
+#define RBIAS2 0x01000100u
+#define RBIAS_ROW0 (64 * 8 * 256)
 // mean2 of four byte pairs (RTL:750-757): (a + b + 1) >> 1 == (a | b) - ((a ^ b) >> 1) per byte; the subtraction never borrows
 // across bytes.  One LOP3 less than the compiler's expansion of __vavgu4.
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
@@ -196,6 +201,7 @@ struct K1Args {
     int write_rec;                                          // 0 for the last frame of a GOP: its reconstruction is never read
     unsigned *ctr, *ctr_next;                               // work counter of this launch (zero on entry) / of the next one (zeroed here)
     uint32_t mw, mh;                                        // ceil(2^32/mbw), ceil(2^32/mbh): index -> (GOP, row, column) without divisions
+    uint32_t k1024;                                         // = 1024, opaque to the compiler (keeps a multiply-add on the FMA pipe)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,9 +209,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatil
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// A TMA that faults never completes its mbarrier: the wait is bounded (each try_wait already blocks for a hardware time slice) and
+// traps, so a bad tensor map surfaces as a launch error (M2V_ECUDA) instead of a hung stream.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
@@ -233,11 +245,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     typedef WarpSmemT<PFRAME> WarpSmem;
     typedef StageSmemT<PFRAME> StageSmem;
     QEntry *const qt = reinterpret_cast<QEntry *>(smem_raw + sizeof(WarpSmem) * K1_WARPS);   // 64 entries after the warps' areas
-    unsigned long long *const bars = reinterpret_cast<unsigned long long *>(qt + 64) + 2 * (threadIdx.x >> 5);   // one mbarrier per stage
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *const bars0 = reinterpret_cast<unsigned long long *>(qt + 64);                          // one mbarrier per stage and warp
+    // the shuffle from lane 0 tells the compiler that the warp index is warp-uniform: the per-warp shared-memory addresses, the
+    // mbarrier and the TMA issue then live in the uniform datapath instead of vector registers and waterfall loops
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
     if (threadIdx.x < 64) qt[threadIdx.x] = d_qtab[p.Q - 1][threadIdx.x];
     __syncthreads();
     WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
+    unsigned long long *const bars = bars0 + 2 * warp;
     const unsigned gwarp = blockIdx.x * K1_WARPS + warp, nwarps = gridDim.x * K1_WARPS;
     if (gwarp >= p.total) return;
     const int W = p.W, CWp = p.CWp;
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     }
     const int g = cur.g, by = cur.by, bx = cur.bx;
     const unsigned mb = (unsigned)(by * p.mbw + bx);
-    const long n = (long)g * (p.P + 1) + p.t;               // frame index inside the batch
+    const unsigned n = (unsigned)(g * (p.P + 1) + p.t);     // frame index inside the batch
     const int Y0 = by * 16, X0 = bx * 16;
     StageSmem &S = s.st[stg];
     int32_t *tmp;
@@ -345,11 +360,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
             // key = SAD<<10 | (R-dy)<<5 | (R-dx): minimum = smallest SAD, ties -> largest dy, then largest dx
             // (RTL:1696-1710).  SAD >= 4096 disqualifies (RTL:1669-1670)  <=>  key >= 1<<22, checked once at
             // the end.  The border rule (RTL:1642-1645) is warp-uniform in dy and per-lane in dx.
+            // The key is linear in the two half-row sums, so each half forms acc*1024 + half of the dy term (one IMAD
+            // with an immediate) BEFORE the exchange and the sum and the running minimum are one VIADDMNMX; the dx term
+            // is the same for every dy of a lane and is added once after the minimum.
             uint32_t best = 0xFFFFFFFFu;
-            const int dx = (lane & 15) - R;
             auto fold = [&](int dyi) {
-                const uint32_t tot = acc[dyi] + __shfl_xor_sync(FULL, acc[dyi], 16);
-                best = min(best, tot * 1024u + (uint32_t)(((2 * R - dyi) << 5) + R - dx));
+                const uint32_t k = acc[dyi] * p.k1024 + (uint32_t)((2 * R - dyi) << 4);   // IMAD (FMA pipe); a literal 1024 becomes an ALU-pipe LEA
+                best = min(best, k + __shfl_xor_sync(FULL, k, 16));
             };
             if (by != 0) {                                   // dy < 0 is forbidden in the top block row (two warp-uniform branches)
 #pragma unroll
@@ -360,91 +377,88 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
                 for (int dyi = R + 1; dyi <= 2 * R; dyi++) fold(dyi);
             }
+            const int dx = lane - R;
+            best += (uint32_t)(2 * R - lane);                // R - dx; only lanes 0..2R (half 0, one per dx) take part below
             if (lane > 2 * R || (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0)) best = 0xFFFFFFFFu;
             best = __reduce_min_sync(FULL, best);
             if (best < (1u << 22)) { fmvy = R - (int)((best >> 5) & 31); fmvx = R - (int)(best & 31); }
         }
 
-        // ---- half-pel refinement + intra/inter decision (RTL:1743-1816).  lane = 2*y + half. ----
-        const int y = lane >> 1, half = lane & 1;
-        const uint32_t c0 = S.curY[y][half * 2], c1 = S.curY[y][half * 2 + 1];
-        uint32_t cand[9][2];
+        // ---- half-pel refinement + intra/inter decision (RTL:1743-1816).  lane = q + 4*j: the lane owns the 4-byte quarter q
+        //      of the two rows a = 2j and b = 2j+1 and builds the shifted words and pair sums of the FOUR window rows
+        //      a-1, a, b, b+1 once.  The vertical and diagonal half-pel planes are shared between neighbouring rows
+        //      (candidate "down" of row a IS candidate "up" of row b), so three row pairs serve both rows: 4 row builds and
+        //      3 pair builds per 2 rows, where a lane that owns one row needs 3 and 2 per row.
+        const int q = lane & 3, j = lane >> 2;
+        const uint32_t ca = S.curY[2 * j][q], cb = S.curY[2 * j + 1][q];
+        uint32_t zz[4], V[3], DL[3], DR[3], c3a, c5a, c3b, c5b;       // full-pel rows; mean2 up/down; mean4 left/right diagonals; mean2 left/right
         {
-            const int wr0 = (R + 1) + fmvy + y - 1;
-            const int o = 15 + fmvx + 8 * half, wi = o >> 2, sh = (o & 3) * 8;
-            uint32_t zm[3][2], zz[3][2], zp[3][2];           // bytes x-1, x, x+1 of rows y-1,y,y+1
+            const int wr0 = R + fmvy + 2 * j;                          // window row of picture row a-1
+            const int o = 15 + fmvx + 4 * q, wi = o >> 2, sh = (o & 3) * 8;   // byte of pixel x-1, x = 4q
+            uint32_t pmL[4], pmH[4], ppL[4], ppH[4];                   // pair sums (x-1,x) and (x,x+1) as packed halfwords
 #pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
+            for (int rr = 0; rr < 4; rr++) {
                 const uint32_t *row = S.winY[wr0 + rr];
-                uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2], w3 = row[wi + 3];
-                uint32_t v0 = fsr(w0, w1, sh), v1 = fsr(w1, w2, sh), v2 = fsr(w2, w3, sh);
-                zm[rr][0] = v0; zm[rr][1] = v1;
-                zz[rr][0] = fsr(v0, v1, 8); zz[rr][1] = fsr(v1, v2, 8);
-                zp[rr][0] = fsr(v0, v1, 16); zp[rr][1] = fsr(v1, v2, 16);
+                const uint32_t w0 = row[wi], w1 = row[wi + 1], w2 = row[wi + 2];
+                const uint32_t v0 = fsr(w0, w1, sh), v1 = fsr(w1, w2, sh);    // bytes x-1..x+2, x+3..x+6
+                const uint32_t z = fsr(v0, v1, 8), zp = fsr(v0, v1, 16);      // bytes x..x+3, x+1..x+4
+                zz[rr] = z;
+                // mean4 (RTL:1751, 764) = (pair sum of the upper row + pair sum of the lower row + 1) >> 2
+                const uint32_t el = exlo(z), eh = exhi(z);
+                pmL[rr] = exlo(v0) + el; pmH[rr] = exhi(v0) + eh;
+                ppL[rr] = exlo(zp) + el; ppH[rr] = exhi(zp) + eh;
+                if (rr == 1) { c3a = avg4(v0, z); c5a = avg4(z, zp); }            // mean2 left / right (RTL:1749)
+                if (rr == 2) { c3b = avg4(v0, z); c5b = avg4(z, zp); }
             }
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                cand[4][k] = zz[1][k];                                            // f_Y_hlf even,even
-                cand[3][k] = avg4(zm[1][k], zz[1][k]);                        // mean2 left   (RTL:1749)
-                cand[5][k] = avg4(zz[1][k], zp[1][k]);                        // mean2 right
-                cand[1][k] = avg4(zz[0][k], zz[1][k]);                        // mean2 up     (RTL:1750)
-                cand[7][k] = avg4(zz[1][k], zz[2][k]);                        // mean2 down
-                // diagonals: mean4 with +1 rounding (RTL:1751, 764) on packed halfwords
-                uint32_t pm[3][2], pp[3][2];                                      // pair sums (x-1,x) and (x,x+1), per row
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) {
-                    uint32_t zl = exlo(zz[rr][k]), zh = exhi(zz[rr][k]);
-                    pm[rr][0] = exlo(zm[rr][k]) + zl; pm[rr][1] = exhi(zm[rr][k]) + zh;
-                    pp[rr][0] = exlo(zp[rr][k]) + zl; pp[rr][1] = exhi(zp[rr][k]) + zh;
-                }
-                // every diagonal contains the middle row: its pair sums carry the +1 of the rounding for all four
-                pm[1][0] += 0x00010001u; pm[1][1] += 0x00010001u; pp[1][0] += 0x00010001u; pp[1][1] += 0x00010001u;
-                cand[0][k] = pack4((pm[0][0] + pm[1][0]) >> 2, (pm[0][1] + pm[1][1]) >> 2);
-                cand[2][k] = pack4((pp[0][0] + pp[1][0]) >> 2, (pp[0][1] + pp[1][1]) >> 2);
-                cand[6][k] = pack4((pm[1][0] + pm[2][0]) >> 2, (pm[1][1] + pm[2][1]) >> 2);
-                cand[8][k] = pack4((pp[1][0] + pp[2][0]) >> 2, (pp[1][1] + pp[2][1]) >> 2);
+            for (int k = 0; k < 3; k++) {
+                V[k] = avg4(zz[k], zz[k + 1]);                                  // mean2 up / down (RTL:1750)
+                DL[k] = pack4(m4h(pmL[k] + pmL[k + 1]), m4h(pmH[k] + pmH[k + 1]));   // the +1 rides in the three-input add
+                DR[k] = pack4(m4h(ppL[k] + ppL[k + 1]), m4h(ppH[k] + ppH[k + 1]));
             }
         }
         int key[10];
         {
-            const bool xn = (bx == 0 || fmvx == -R), xp = (bx == p.mbw - 1 || fmvx == R);
-            const bool yn = (by == 0 || fmvy == -R), yp = (by == p.mbh - 1 || fmvy == R);
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-                uint32_t sd = sad4(cand[i][0], c0, sad4(cand[i][1], c1, 0));
-                sd = __reduce_add_sync(FULL, sd);
-                const int cy = i / 3 - 1, cx = i % 3 - 1;
-                bool dis = (cx < 0 && xn) || (cx > 0 && xp) || (cy < 0 && yn) || (cy > 0 && yp);   // RTL:1757-1760
-                // {f_over, f_diff}: any key >= 4096 loses against the intra key (<= 4095) and against every valid
-                // candidate, and ties among keys >= 4096 never decide anything, so the overflowed SAD itself
-                // serves as its own "disabled" key (RTL:1784-1785, 1795-1804)
-                key[i] = dis ? 0x10000 : (int)sd;
-            }
+            // a disabled candidate (RTL:1757-1760) gets 0x800 per lane = 0x10000 per macroblock on top of its SAD through the
+            // initial accumulator.  {f_over, f_diff}: any key >= 4096 loses against the intra key (<= 4095) and against every
+            // valid candidate, and ties among keys >= 4096 never decide anything (RTL:1784-1785, 1795-1804).
+            const uint32_t kxn = (bx == 0 || fmvx == -R) ? 0x800u : 0u, kxp = (bx == p.mbw - 1 || fmvx == R) ? 0x800u : 0u;
+            const uint32_t kyn = (by == 0 || fmvy == -R) ? 0x800u : 0u, kyp = (by == p.mbh - 1 || fmvy == R) ? 0x800u : 0u;
+            auto sadk = [&](uint32_t xa, uint32_t xb, uint32_t k0) { return (int)__reduce_add_sync(FULL, sad4(xa, ca, sad4(xb, cb, k0))); };
+            key[0] = sadk(DL[0], DL[1], kxn + kyn); key[1] = sadk(V[0], V[1], kyn); key[2] = sadk(DR[0], DR[1], kxp + kyn);
+            key[3] = sadk(c3a, c3b, kxn);           key[4] = sadk(zz[1], zz[2], 0); key[5] = sadk(c5a, c5b, kxp);
+            key[6] = sadk(DL[1], DL[2], kxn + kyp); key[7] = sadk(V[1], V[2], kyp); key[8] = sadk(DR[1], DR[2], kxp + kyp);
             // intra key: pixel sum + sum|pixel-mean|, 16 bit, saturated to 4095 (RTL:1600,1662,1744,1776-1777,1791)
-            uint32_t S = __reduce_add_sync(FULL, sad4(c0, 0, sad4(c1, 0, 0)));
+            uint32_t S = __reduce_add_sync(FULL, sad4(ca, 0, sad4(cb, 0, 0)));
             uint32_t m = (S >> 8) & 0xFF; m |= m << 8; m |= m << 16;
-            uint32_t D = __reduce_add_sync(FULL, sad4(c0, m, sad4(c1, m, 0)));
+            uint32_t D = __reduce_add_sync(FULL, sad4(ca, m, sad4(cb, m, 0)));
             uint32_t T = (S + D) & 0xFFFF;
             key[9] = T < 4096u ? (int)T : 4095;
         }
         const int w = find_min10(key);
         inter = (w != 9);
-        const int hy = inter ? w / 3 - 1 : 0, hx = inter ? w % 3 - 1 : 0;
-        mvy = 2 * fmvy + hy; mvx = 2 * fmvx + hx;              // RTL:1827-1828
 
-        // ---- luma prediction + residual (RTL:1891-1897, 1980-2002) -----------------------------
-        uint32_t p0 = 0x80808080u, p1 = 0x80808080u;
-        if (inter) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) if (w == i) { p0 = cand[i][0]; p1 = cand[i][1]; }
+        // ---- luma prediction + residual (RTL:1891-1897, 1980-2002).  w is warp-uniform: one branch instead of nine selects
+        uint32_t pa = 0x80808080u, pb = 0x80808080u;
+        int hy = 0, hx = 0;
+        switch (w) {
+            case 0: pa = DL[0]; pb = DL[1]; hy = -1; hx = -1; break;
+            case 1: pa = V[0];  pb = V[1];  hy = -1; break;
+            case 2: pa = DR[0]; pb = DR[1]; hy = -1; hx = 1; break;
+            case 3: pa = c3a;   pb = c3b;   hx = -1; break;
+            case 4: pa = zz[1]; pb = zz[2]; break;
+            case 5: pa = c5a;   pb = c5b;   hx = 1; break;
+            case 6: pa = DL[1]; pb = DL[2]; hy = 1; hx = -1; break;
+            case 7: pa = V[1];  pb = V[2];  hy = 1; break;
+            case 8: pa = DR[1]; pb = DR[2]; hy = 1; hx = 1; break;
+            default: break;                                            // intra: predictor 128, vector 0
         }
+        mvy = 2 * fmvy + hy; mvx = 2 * fmvx + hx;                      // RTL:1827-1828
         {
-            const int tile = (y >> 3) * 2 + half, r = y & 7;
-            *(uint2 *)&s.pred[tile][r * 8] = make_uint2(p0, p1);
-            uint4 rv;
-            rv.x = __vsub2(exlo(c0), exlo(p0)); rv.y = __vsub2(exhi(c0), exhi(p0));
-            rv.z = __vsub2(exlo(c1), exlo(p1)); rv.w = __vsub2(exhi(c1), exhi(p1));
-            *(uint4 *)&s.res[tile][r * 8] = rv;
+            const int tile = (j >> 2) * 2 + (q >> 1), e = ((2 * j) & 7) * 8 + 4 * (q & 1);
+            *(uint32_t *)&s.pred[tile][e] = pa; *(uint32_t *)&s.pred[tile][e + 8] = pb;
+            *(uint2 *)&s.res[tile][e] = make_uint2(exlo(ca) + RBIAS2 - exlo(pa), exhi(ca) + RBIAS2 - exhi(pa));
+            *(uint2 *)&s.res[tile][e + 8] = make_uint2(exlo(cb) + RBIAS2 - exlo(pb), exhi(cb) + RBIAS2 - exhi(pb));
         }
         // ---- chroma prediction + residual (RTL:1847-1888, 1899-1916).  lane = comp*16 + y*2 + half.
         {
@@ -466,8 +480,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                 else pc = a0;
             }
             *(uint32_t *)&s.pred[4 + comp][cyy * 8 + ch * 4] = pc;
-            uint2 rv; rv.x = __vsub2(exlo(cc), exlo(pc)); rv.y = __vsub2(exhi(cc), exhi(pc));
-            *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = rv;
+            *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = make_uint2(exlo(cc) + RBIAS2 - exlo(pc), exhi(cc) + RBIAS2 - exhi(pc));
         }
     } else {
         // I-frame: every macroblock intra, predictor 128, vector 0 (RTL:1820-1825, 1894-1903)
@@ -475,15 +488,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         const uint32_t c0 = S.curY[y][half * 2], c1 = S.curY[y][half * 2 + 1], pz = 0x80808080u;
         const int tile = (y >> 3) * 2 + half, r = y & 7;
         *(uint2 *)&s.pred[tile][r * 8] = make_uint2(pz, pz);
-        uint4 rv;
-        rv.x = __vsub2(exlo(c0), exlo(pz)); rv.y = __vsub2(exhi(c0), exhi(pz));
-        rv.z = __vsub2(exlo(c1), exlo(pz)); rv.w = __vsub2(exhi(c1), exhi(pz));
-        *(uint4 *)&s.res[tile][r * 8] = rv;
+        constexpr uint32_t kz = RBIAS2 - 0x00800080u;             // biased residual against the predictor 128
+        *(uint4 *)&s.res[tile][r * 8] = make_uint4(exlo(c0) + kz, exhi(c0) + kz, exlo(c1) + kz, exhi(c1) + kz);
         const int comp = lane >> 4, cyy = (lane >> 1) & 7, ch = lane & 1;
         const uint32_t cc = s.curC[comp][cyy][ch];
         *(uint32_t *)&s.pred[4 + comp][cyy * 8 + ch * 4] = pz;
-        uint2 rc; rc.x = __vsub2(exlo(cc), exlo(pz)); rc.y = __vsub2(exhi(cc), exhi(pz));
-        *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = rc;
+        *(uint2 *)&s.res[4 + comp][cyy * 8 + ch * 4] = make_uint2(exlo(cc) + kz, exhi(cc) + kz);
     }
     __syncwarp();
 
@@ -503,9 +513,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         int x[8], o[8];
         {                                                        // rows: A = R * DCTM^T (RTL:2029-2036)
             uint4 rv = *(const uint4 *)&s.res[tile][v * 8];
-            x[0] = (int16_t)(rv.x & 0xFFFF); x[1] = (int32_t)rv.x >> 16; x[2] = (int16_t)(rv.y & 0xFFFF); x[3] = (int32_t)rv.y >> 16;
-            x[4] = (int16_t)(rv.z & 0xFFFF); x[5] = (int32_t)rv.z >> 16; x[6] = (int16_t)(rv.w & 0xFFFF); x[7] = (int32_t)rv.w >> 16;
+            x[0] = (int)(rv.x & 0xFFFF); x[1] = (int)(rv.x >> 16); x[2] = (int)(rv.y & 0xFFFF); x[3] = (int)(rv.y >> 16);
+            x[4] = (int)(rv.z & 0xFFFF); x[5] = (int)(rv.z >> 16); x[6] = (int)(rv.w & 0xFFFF); x[7] = (int)(rv.w >> 16);
             fdct8(x, o);
+            o[0] -= (tile < 6) ? RBIAS_ROW0 : 0;                 // the two dummy tiles stay all-zero (no bias to remove)
 #pragma unroll
             for (int j = 0; j < 8; j++) tt[v * TROW + j] = o[j];
         }
@@ -572,15 +583,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                 nzl = true;
             }
         }
-        const uint32_t nzm = __ballot_sync(FULL, nzl);
-        if (round == 0) { for (int k = 0; k < 4; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (32 >> k) : 0; }
-        else { for (int k = 0; k < 2; k++) cbp |= (((nzm >> (8 * k)) & 0xFF) || !inter) ? (2 >> k) : 0; }      // bits 16..31: the dummies
+        // cbp bit of this lane's tile (Y00 = 32 ... V = 1; 0 for the dummy tiles 6 and 7): one REDUX.OR gives the coded tiles
+        const uint32_t tb = 0x20u >> tile;
+        const uint32_t nzm = __reduce_or_sync(FULL, nzl ? tb : 0u);
+        cbp |= (int)nzm;
         // A tile whose levels are all zero reconstructs to exactly the prediction (all-zero input gives
         // (128)>>8 = 0 after the row pass and (8192)>>14 = 0 after the column pass), so its inverse
         // transform is skipped; the decision is per 8-lane group, and when no tile of the round holds a level
         // (the usual case in a well-predicted picture) the whole inverse part is one uniform branch.
         if (nzm) {
-            const bool inv = (nzm >> (8 * (lane >> 3))) & 0xFF;
+            const bool inv = (nzm & tb) != 0;
             __syncwarp();                                    // all column reads of A done before overwrite
             if (inv) {
                 if (inter && !maybe) {
@@ -624,8 +636,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                 *(uint2 *)(oY + (unsigned)(ysz + (comp * (p.H >> 1) + by * 8 + cyy) * CWp + bx * 8)) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
             }
         }
-        const size_t mbi = (size_t)n * p.nmb + mb;
-        uint2 *dst = (uint2 *)(p.coefs + mbi * 384);
+        const unsigned mbi = n * (unsigned)p.nmb + mb;           // < 2^25 (m2v_launch_k1 bounds the chunk)
+        uint2 *dst = (uint2 *)(p.coefs + (size_t)mbi * 384);
         // a tile whose cbp bit is clear holds no level and K2 never reads it (RTL:2799, 2804, 2828): not written
 #pragma unroll
         for (int k = 0; k < 3; k++)
@@ -681,21 +693,38 @@ bool m2v_make_tmaps(M2VBatch &b) {
     return true;
 }
 
+template <int VL, bool PF> static constexpr size_t k1_smem() { return sizeof(WarpSmemT<PF>) * K1_WARPS + 64 * sizeof(QEntry) + 16 * K1_WARPS; }
+
+// Per-DEVICE launch configuration (the dynamic shared-memory attribute and the occupancy are properties of a device's
+// context): called by m2v_create on every device a handle owns, with that device current.  Returns the persistent grid
+// sizes = every CTA the device can hold at once.
+template <int VL, bool PF> static cudaError_t k1_setup_t(int *grid_cap) {
+    cudaError_t e = cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<VL, PF>());
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess || (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    // P-frame kernel: 3 CTAs of 8 warps per SM (<= 80 registers, 8.4 KB of shared memory per warp; 4x7 warps at 72
+    // registers measured slower); I-frame kernel: 4 CTAs (64 registers, 5.1 KB per warp)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_mb_encode<VL, PF>, K1_WARPS * 32, k1_smem<VL, PF>()) != cudaSuccess || per_sm < 1) per_sm = PF ? 3 : 4;
+    *grid_cap = sms * per_sm;
+    return cudaSuccess;
+}
+cudaError_t m2v_k1_setup(int VL, int *grid_cap_i, int *grid_cap_p) {
+    cudaError_t e = k1_setup_t<1, false>(grid_cap_i);
+    if (e != cudaSuccess) return e;
+    switch (VL) {
+        case 1: return k1_setup_t<1, true>(grid_cap_p);
+        case 2: return k1_setup_t<2, true>(grid_cap_p);
+        default: return k1_setup_t<3, true>(grid_cap_p);
+    }
+}
+
 template <int VL, bool PF>
 static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream_t st) {
-    const size_t smem = sizeof(WarpSmemT<PF>) * K1_WARPS + 64 * sizeof(QEntry) + 16 * K1_WARPS;
-    static int grid_cap = 0;                                      // persistent grid = every CTA the device can hold at once
-    if (!grid_cap) {
-        cudaFuncSetAttribute(k1_mb_encode<VL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 0, per_sm = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // P-frame kernel: 3 CTAs of 8 warps per SM (80 registers, 8.3 KB of shared memory per warp; 4x7 warps at 72
-        // registers measured slower); I-frame kernel: 4 CTAs (64 registers, 5.1 KB per warp)
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_mb_encode<VL, PF>, K1_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = PF ? 3 : 4;
-        grid_cap = sms * per_sm;
-    }
     unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
-    if (grid > (unsigned)grid_cap) grid = grid_cap;
-    k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, smem, st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
+    const unsigned cap = (unsigned)(PF ? b.k1_grid_cap_p : b.k1_grid_cap_i);
+    if (grid > cap) grid = cap;
+    k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, k1_smem<VL, PF>(), st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
 }
 
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st) {
@@ -707,6 +736,7 @@ void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStr
     a.total = (unsigned)(ngops_t * b.g.nmb);
     a.write_rec = t < b.g.P;
     a.ctr = b.k1_ctr + (seq & 1); a.ctr_next = b.k1_ctr + ((seq & 1) ^ 1);
+    a.k1024 = 1024u;
     a.mw = (uint32_t)((0x100000000ull + b.g.mbw - 1) / b.g.mbw); a.mh = (uint32_t)((0x100000000ull + b.g.mbh - 1) / b.g.mbh);
     const int refk = (t & 1) ^ 1;
     if (t == 0) { launch_k1_t<1, false>(a, b, refk, st); return; }
@@ -752,6 +782,7 @@ struct K2Args {
     uint32_t *mb_bits; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
     uint32_t *out;
     int mbw, mbh, nmb, P; long n0; long total;
+    long F; unsigned long long cap_words;                     // write pass: frames in the batch, capacity of `out` in 32-bit words
 };
 
 // K2: ONE THREAD PER MACROBLOCK, lanes of a warp = consecutive macroblocks (RTL:2718-2847).
@@ -864,6 +895,7 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128) k2_vlc(K2Args p) {
     const long gw = (long)blockIdx.x * 128 + threadIdx.x;
     if (gw >= p.total) return;
+    if (WRITE && M2V_BODY_WORDS(__ldg(&p.frame_off[p.F])) > p.cap_words) return;   // body larger than the buffer: the host re-runs the batch
     const long f = gw / p.nmb;
     const int mb = (int)(gw - f * p.nmb), by = mb / p.mbw, bx = mb - by * p.mbw;
     const int k = (int)((p.n0 + f) % (p.P + 1));
@@ -888,6 +920,7 @@ void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
     a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
     a.frame_off = b.frame_off; a.out = b.out_words;
     a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
+    a.F = b.F; a.cap_words = b.out_cap_words;
     const unsigned grid = (unsigned)((a.total + 127) / 128);
     if (write) k2_vlc<true><<<grid, 128, 0, st>>>(a); else k2_vlc<false><<<grid, 128, 0, st>>>(a);
 }
@@ -972,9 +1005,10 @@ void m2v_launch_k3_scan(const M2VBatch &b, cudaStream_t st) {
 // K4: GOP / picture / slice headers (RTL:2645-2656, 2666-2682, 2704-2710).  One thread per slice.
 // ------------------------------------------------------------------------------------------------
 __global__ void k4_headers(uint32_t *out, const unsigned long long *frame_off, const uint32_t *slice_off,
-                           long F, long n0, int P, int mbh, int Q) {
+                           long F, long n0, int P, int mbh, int Q, unsigned long long cap_words) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F * mbh) return;
+    if (M2V_BODY_WORDS(frame_off[F]) > cap_words) return;
     const long f = i / mbh; const int sl = (int)(i % mbh);
     const long n = n0 + f; const int k = (int)(n % (P + 1));
     unsigned long long pos = 8ull * frame_off[f];
@@ -998,5 +1032,19 @@ __global__ void k4_headers(uint32_t *out, const unsigned long long *frame_off, c
 
 void m2v_launch_headers(const M2VBatch &b, cudaStream_t st) {
     const long n = b.F * b.g.mbh;
-    k4_headers<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.out_words, b.frame_off, b.slice_off, b.F, b.n0, b.g.P, b.g.mbh, b.g.Q);
+    k4_headers<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.out_words, b.frame_off, b.slice_off, b.F, b.n0, b.g.P, b.g.mbh, b.g.Q, b.out_cap_words);
+}
+
+// Zeroes exactly the words the body will occupy (the write pass ORs into them), sized on the DEVICE from the scan's total: no
+// host round trip between the scans and the write pass.  A body that does not fit the buffer is left alone (and K4 / K2 write
+// skip it): the host sees total > capacity after the batch, grows the buffer and runs the batch again.
+__global__ void __launch_bounds__(256) k_zero_body(uint4 *out, const unsigned long long *total, unsigned long long cap_words) {
+    const unsigned long long words = M2V_BODY_WORDS(*total);
+    if (words > cap_words) return;
+    const unsigned long long n4 = (words + 3) / 4;             // the buffer is allocated in multiples of 16 bytes
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = make_uint4(0, 0, 0, 0);
+}
+void m2v_launch_zero_body(const M2VBatch &b, cudaStream_t st) {
+    k_zero_body<<<592, 256, 0, st>>>((uint4 *)b.out_words, b.frame_off + b.F, b.out_cap_words);
 }

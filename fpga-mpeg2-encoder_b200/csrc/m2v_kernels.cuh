@@ -32,19 +32,26 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     uint32_t *frame_bytes;     // [F]       slice-area bytes of the frame
     unsigned long long *frame_off; // [F+1] byte offset of each frame in the body; [F] = total
     uint32_t *out_words;       // body, big-endian bit order packed into bytes
+    size_t out_cap_words;      // capacity of out_words (32-bit words, a multiple of 4); a larger body is not written (see k_zero_body)
+    int k1_grid_cap_i, k1_grid_cap_p;   // persistent K1 grid sizes on the device this batch runs on (m2v_k1_setup)
     unsigned *k1_ctr;          // [2] work counters of K1's dynamic macroblock distribution; launch `seq` uses [seq&1] and
                                // zeroes the other one for the launch after it (both zero before the first launch)
 };
+#define M2V_BODY_WORDS(total_bytes) ((total_bytes) / 4 + 4)   // words the body needs: its bytes, rounded up, plus slack for the last RED.OR
 #define M2V_K1_MAX_MBS (1l << 25)   // macroblocks per K1 launch: bound of the division-free index decode
 
 bool m2v_make_tmaps(M2VBatch &b);
 // K1: one warp per macroblock; step t = frame index inside every GOP of the batch; seq = running number of the K1
 // launches on this stream (selects the work counter)
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st);
-// K2: one warp per macroblock; count = bit lengths only, write = emit into out_words
+// K2: one thread per macroblock; count = bit lengths only, write = emit into out_words
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st);
 // K3: slice/frame/batch scans of the bit lengths; then headers
 void m2v_launch_k3_scan(const M2VBatch &b, cudaStream_t st);
 void m2v_launch_headers(const M2VBatch &b, cudaStream_t st);
+// zero the body's words on the device, sized from frame_off[F] (no host round trip)
+void m2v_launch_zero_body(const M2VBatch &b, cudaStream_t st);
+// per-device K1 configuration (shared-memory attribute, persistent grid sizes); the device must be current
+cudaError_t m2v_k1_setup(int VL, int *grid_cap_i, int *grid_cap_p);
 // one-time upload of the VLC / quantiser tables for this Q_LEVEL
 cudaError_t m2v_upload_tables(int Q);

@@ -4,10 +4,12 @@
  * RTL/mpeg2encoder.v:10-38 (semantics README.md:90-234), as driven by SIM/tb_mpeg2encoder.v:95-128
  * (instance) and :206-266 (stimulus / sink).  Plain C, plain pointers and sizes; no C++/torch types.
  * Every function returns M2V_OK (0) or a negative M2V_E* code; nothing throws across the ABI.
- * A handle is NOT thread-safe (the RTL is one clock domain, one sequence at a time).
+ * A handle is NOT thread-safe (the RTL is one clock domain, one sequence at a time): one host thread per
+ * handle.  Inside, the library owns the CUDA streams, the pinned staging / output memory and one worker
+ * thread per device, for 1..8 devices (m2v_create: the device current at the call; m2v_create_multi:
+ * devices 0..ndev-1).  Several handles, on the same or on different devices, can live in one process.
  *
- * All compute runs on the CUDA device that is current when m2v_create() is called; there is no
- * CPU fallback - m2v_create() fails with M2V_ENODEV when no sm_100 device is usable.
+ * There is no CPU fallback - m2v_create() fails with M2V_ENODEV when no sm_100 device is usable.
  */
 #ifndef M2VENC_H
 #define M2VENC_H
@@ -32,6 +34,11 @@ enum {
 /* rstn + static parameters (RTL:11-14; README.md:79-84): XL,YL in 4..7, VECTOR_LEVEL in 1..3,
  * Q_LEVEL in 1..4.  Equivalent to instantiating the module and pulsing reset (README.md:96). */
 int  m2v_create(int XL, int YL, int VECTOR_LEVEL, int Q_LEVEL, m2v_encoder **out);
+/* The same module instance spread over `ndev` GPUs (devices 0..ndev-1, 1 <= ndev <= 8) of this process: the streaming
+ * calls below deal whole closed GOPs (RTL:2645-2656, 1820-1825) to the devices in batches and m2v_pull / m2v_drain
+ * return ONE ordered word stream, byte-identical to the single-device one (RTL:10-38: one instance, one stream). */
+int  m2v_create_multi(int ndev, int XL, int YL, int VECTOR_LEVEL, int Q_LEVEL, m2v_encoder **out);
+int  m2v_device_count(const m2v_encoder *e);
 void m2v_destroy(m2v_encoder *e);
 const char *m2v_last_error(const m2v_encoder *e);
 
@@ -45,11 +52,16 @@ int  m2v_push4(m2v_encoder *e, const uint8_t Y[4], const uint8_t U[4], const uin
 
 /* Bulk form of the same stimulus: nframes planar yuv444p frames (Y plane, U plane, V plane per
  * frame, exactly as TB:210-218 loads them) of the CLAMPED geometry, in HOST memory.  Must start on
- * a frame boundary.  The library copies what it needs before returning. */
+ * a frame boundary.  The library has copied what it needs when the call returns (the buffer can be
+ * reused at once); the kernels of the last batches may still be running then and overlap the caller's
+ * next read.  Memory from m2v_alloc_host (or registered with m2v_register_host) is copied at PCIe
+ * rate; pageable memory works but goes through the driver's bounce buffer.  nframes == 0 is a no-op
+ * (no i_en, the sequence is not armed: RTL:1060-1065). */
 int  m2v_push_frames(m2v_encoder *e, const uint8_t *yuv444p, long nframes);
 
 /* i_sequence_stop (RTL:1082-1083,1090-1091): an unfinished frame is padded with Y=0,U=V=0x80
- * (RTL:1036-1037,1049-1056); the end code and the final padded word are produced. */
+ * (RTL:1036-1037,1049-1056); the end code and the final padded word are produced.  Returns when every
+ * batch has been encoded, i.e. the whole stream can be pulled. */
 int  m2v_stop(m2v_encoder *e);
 
 /* o_sequence_busy (RTL:1095): 1 from the first pixel until the o_last word has been pulled. */
@@ -61,7 +73,8 @@ int  m2v_busy(const m2v_encoder *e);
 int  m2v_pull(m2v_encoder *e, uint8_t out[32], int *last);
 
 /* Bulk pull: copies as many whole available words as fit in cap; *n = bytes written;
- * *last = 1 when the o_last word was among them. */
+ * *last = 1 when the o_last word was among them.  Never blocks: words of batches still on a device
+ * are simply not available yet (all of them are after m2v_stop). */
 int  m2v_drain(m2v_encoder *e, uint8_t *dst, size_t cap, size_t *n, int *last);
 
 /* ---- device-resident bulk path (used for GOP sharding across GPUs and by bench.py) -----------
@@ -71,7 +84,10 @@ int  m2v_drain(m2v_encoder *e, uint8_t *dst, size_t cap, size_t *n, int *last);
  * Produces the byte-aligned GOP/picture/slice layers of those frames ("body"), i.e. everything
  * between the 34-byte sequence header and the sequence end code.
  *   d_body/body_len : internal DEVICE buffer holding the body, valid until the next call
- * Does not touch the streaming state (begin/push/stop). */
+ * Runs on the handle's first device.  Preconditions: d_yuv444p is 16-byte aligned (the frames are read
+ * by TMA; M2V_EINVAL otherwise); the caller's writes to the frames have completed (the kernels run on
+ * the library's own non-blocking stream, which does not order against the caller's streams: synchronise
+ * first); no streamed batch is in flight (M2V_ESTATE).  Does not touch the streaming state. */
 int  m2v_encode_gops_device(m2v_encoder *e, int mbw, int mbh, int pframes_count,
                             const uint8_t *d_yuv444p, long nframes, long n0,
                             const uint8_t **d_body, size_t *body_len);
@@ -80,6 +96,26 @@ int  m2v_encode_gops_device(m2v_encoder *e, int mbw, int mbh, int pframes_count,
 int  m2v_encode_gops_host(m2v_encoder *e, int mbw, int mbh, int pframes_count,
                           const uint8_t *d_yuv444p, long nframes, long n0,
                           uint8_t *h_body, size_t cap, size_t *body_len);
+
+/* Asynchronous form of m2v_encode_gops_device for callers that shard GOPs over processes and want the body of chunk i
+ * on its way to the host while chunk i+1 is encoded.  Two slots (0/1), each with its own body buffer:
+ *   m2v_gops_submit : queue the whole hot path of a chunk into `slot`; returns at once
+ *   m2v_gops_size   : body length of that chunk - known after the scans, while the write pass is still running
+ *   m2v_gops_fetch  : queue the device->host copy of the body (after the write pass) on the copy-out stream
+ *   m2v_gops_wait   : wait for the chunk's kernels and fetch;  m2v_gops_body : the slot's device buffer
+ * A chunk is at most what one launch sequence takes (m2v_encode_gops_device cuts longer jobs itself). */
+int  m2v_gops_submit(m2v_encoder *e, int mbw, int mbh, int pframes_count, const uint8_t *d_yuv444p, long nframes, long n0, int slot);
+int  m2v_gops_size(m2v_encoder *e, int slot, size_t *body_len);
+int  m2v_gops_fetch(m2v_encoder *e, int slot, uint8_t *h_dst, size_t len);
+int  m2v_gops_wait(m2v_encoder *e, int slot);
+int  m2v_gops_body(m2v_encoder *e, int slot, const uint8_t **d_body);
+
+/* Pinned host memory for frames and streams (host<->device copies at PCIe rate), and pinning of memory the caller
+ * already owns (a shared-memory arena, an mmap). */
+void *m2v_alloc_host(size_t bytes);
+void  m2v_free_host(void *p);
+int  m2v_register_host(void *p, size_t bytes);
+int  m2v_unregister_host(void *p);
 
 /* Host-side framing helpers (RTL:2596-2617; RTL:2621-2628 + 2932-2937). */
 int  m2v_sequence_header(int mbw, int mbh, uint8_t out34[34]);
@@ -91,14 +127,18 @@ int  m2v_finish_stream(uint8_t *buf, size_t len, size_t cap, size_t *total);
  * of `coefs` is only meaningful where the macroblock's cbp bit is set: uncoded tiles are not written. */
 int  m2v_debug_copy(m2v_encoder *e, uint32_t *mbinfo, int16_t *coefs, long nframes_times_nmb);
 /* Kernel launch counter (bench.py "gpu_launches") and device time in ms (CUDA events on the
- * launching stream) of the last encode_gops call: idx 0 = all mb_encode (K1) launches, 1 = vlc count,
- * 2 = scans + size read-back + headers, 3 = vlc write, 4 = first launch -> last kernel end. */
+ * launching stream) of the last encode_gops call (or, for the m2v_gops_* form, accumulated by m2v_gops_wait): idx 0 = all
+ * mb_encode (K1) launches, 1 = vlc count, 2 = scans + body zeroing + headers, 3 = vlc write, 4 = first launch -> last kernel end. */
 long m2v_launch_count(const m2v_encoder *e);
 /* Test knob: overrides the sizes the library picks by itself - the streaming flush threshold (frames per batch of
  * m2v_push*; rounded down to whole GOPs, at least one) and the frames per internal chunk of m2v_encode_gops_* -
  * so that the multi-batch / multi-chunk paths can be driven with small clips.  0 = automatic.  The stream does not
  * depend on either value (closed GOPs, RTL:2645-2656). */
 int  m2v_set_limits(m2v_encoder *e, long batch_frames, long chunk_frames);
+/* Test knob: bytes of body buffer reserved per macroblock (default 192, several times a typical body).  A batch whose
+ * body does not fit is detected after its scans, the buffer grows to what the scan asked for and the batch runs again;
+ * a tiny value forces that path. */
+int  m2v_set_body_reserve(m2v_encoder *e, long bytes_per_macroblock);
 int  m2v_kernel_ms(const m2v_encoder *e, float ms[5]);
 int  m2v_set_timing(m2v_encoder *e, int enable);
 

@@ -185,6 +185,48 @@ def test_config3_and_config4_sizes_sample_gop(pkg, ob, synth):
     assert out[:l2].tobytes() == want
 
 
+def test_full_gop_1920x1152_parameter_sweep(pkg, ob, synth):
+    """BASELINE config 4 is a Q_LEVEL sweep at 1920x1152: one FULL 16-frame GOP for Q_LEVEL 1, 3, 4 (VECTOR_LEVEL=3) and for
+    VECTOR_LEVEL 1, 2 (Q_LEVEL=2) against the oracle.  k1_mb_encode<1,true> / <2,true> have their own TMA box heights
+    (18+4*VL window rows) and search ranges (RTL:1634-1715); the quantisers differ per Q_LEVEL (RTL:2065-2077)."""
+    import threading
+    import torch
+    W, H, P = 1920, 1152, 15
+    fr = synth.s1_pan(20261018, 16, W, H)
+    d = torch.from_numpy(fr).cuda()
+    cases = [(3, 1), (3, 3), (3, 4), (1, 2), (2, 2)]
+    want = {}
+    def work(c):
+        want[c] = ob.encode_range(fr, 32, W // 16, H // 16, P, VL=c[0], Q=c[1])
+    th = [threading.Thread(target=work, args=(c,)) for c in cases]
+    for t in th: t.start()
+    out = np.zeros(64 << 20, np.uint8)
+    got = {}
+    for VL, Q in cases:
+        enc = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=Q)
+        ln = enc.encode_gops_host(d.data_ptr(), 16, 32, W // 16, H // 16, P, out)      # GOP 2 of a longer sequence (time code)
+        got[(VL, Q)] = out[:ln].tobytes()
+        enc.close()
+    for t in th: t.join()
+    for c in cases:
+        assert got[c] == want[c], 'VECTOR_LEVEL=%d Q_LEVEL=%d: %d vs %d bytes' % (c[0], c[1], len(got[c]), len(want[c]))
+
+
+def test_config5_full_gop(pkg, ob, synth):
+    """config 5 (2048x2048, the XL=YL=7 maximum): one FULL I+15P GOP against the oracle, the oracle cut in two threads is
+    not possible inside a GOP, so this is the slowest single oracle call of the suite (~3 s)"""
+    import torch
+    W = H = 2048
+    P = 15
+    fr = synth.s1_pan(20261019, 16, W, H)
+    d = torch.from_numpy(fr).cuda()
+    enc = pkg.Mpeg2Encoder(XL=7, YL=7)
+    out = np.zeros(64 << 20, np.uint8)
+    ln = enc.encode_gops_host(d.data_ptr(), 16, 16, W // 16, H // 16, P, out)
+    enc.close()
+    assert out[:ln].tobytes() == ob.encode_range(fr, 16, W // 16, H // 16, P)
+
+
 def test_config5_maximum_size(pkg, ob, synth):
     """2048x2048 = the largest frame XL=YL=7 allows (config 5): I+2P against the oracle, and the clamp at that
     limit (RTL:985-991): asking for 129x129 macroblocks encodes exactly the 128x128 stream."""
