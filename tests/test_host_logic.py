@@ -83,8 +83,8 @@ def test_ac_table_occupancy_equals_the_rtl_ranges():
 
 def test_byte_simd_identities():
     """the packed-byte forms K1 uses for the RTL's mean2 (RTL:750-757) and mean4 (RTL:760-767), replayed in numpy:
-    avg4(a,b) = (a|b) - (((a^b) & 0xFEFEFEFE) >> 1) per 32-bit word; mean4 on halfword pair sums, +1 folded into one
-    addend, shifted right by 2 WITHOUT a mask, bytes 0 and 2 picked by the byte permute"""
+    avg4(a,b) = (a|b) - (((a^b) & 0xFEFEFEFE) >> 1) per 32-bit word; mean4 from the five horizontal pair sums of six bytes,
+    packed by parity (P02, P13, P24), summed over two rows, times 64 plus 0x00400040, bytes 1 and 3 interleaved"""
     rng = np.random.default_rng(3)
     edge = np.array([0, 1, 2, 127, 128, 254, 255], dtype=np.uint8)
     def words(n):
@@ -96,15 +96,56 @@ def test_byte_simd_identities():
     got = ((wa | wb) - (((wa ^ wb) & np.uint64(0xFEFEFEFE)) >> np.uint64(1))) & np.uint64(0xFFFFFFFF)
     want = ((a.astype(np.uint16) + b + 1) >> 1).astype(np.uint8)
     assert (got.astype('<u4').view(np.uint8).reshape(-1, 4) == want).all()
-    # mean4: four byte planes p,q (row r) and t,u (row r+1); halfword sums of bytes (0,1) and (2,3) as exlo/exhi build them
-    p, q, t, u = words(100000), words(100000)[::-1].copy(), words(100000), words(100000)[::-1].copy()
-    ex = lambda v, i, j: v[:, i].astype(np.uint64) | (v[:, j].astype(np.uint64) << np.uint64(16))
-    for (i, j) in ((0, 1), (2, 3)):
-        s_mid = ex(p, i, j) + ex(q, i, j) + np.uint64(0x00010001)          # the middle row's pair sum carries the +1
-        s = ((s_mid + ex(t, i, j) + ex(u, i, j)) >> np.uint64(2)) & np.uint64(0xFFFFFFFF)
-        b0, b2 = (s & np.uint64(0xFF)).astype(np.uint8), ((s >> np.uint64(16)) & np.uint64(0xFF)).astype(np.uint8)
-        w = lambda k: ((p[:, k].astype(np.uint16) + q[:, k] + t[:, k] + u[:, k] + 1) >> 2).astype(np.uint8)
-        assert (b0 == w(i)).all() and (b2 == w(j)).all()
+    # mean4: rows r0, r1 of six bytes b0..b5 (pixels x-1..x+4); left diagonals use pair sums S0..S3, right ones S1..S4
+    n = 100000
+    r0 = rng.integers(0, 256, (n, 6), dtype=np.uint8); r1 = rng.integers(0, 256, (n, 6), dtype=np.uint8)
+    r0[:49, :] = np.array([[x, y, 255, x, y, 255 - x] for x in edge for y in edge], dtype=np.uint8); r1[:49] = 255 - r0[:49] // 2
+    M = np.uint64(0xFFFFFFFF)
+    def parity(r):
+        u = r.astype(np.uint64)
+        e0, o0 = u[:, 0] | (u[:, 2] << np.uint64(16)), u[:, 1] | (u[:, 3] << np.uint64(16))      # v0 & 0x00FF00FF, prmt(v0, 0x4341)
+        e1, o1 = u[:, 2] | (u[:, 4] << np.uint64(16)), u[:, 3] | (u[:, 5] << np.uint64(16))      # the same of zp
+        return e0 + o0, o0 + e1, e1 + o1
+    A, B = parity(r0), parity(r1)
+    q = [((x + y) * np.uint64(64) + np.uint64(0x00400040)) & M for x, y in zip(A, B)]
+    def perm7351(x, y):                                           # bytes (x.b1, y.b1, x.b3, y.b3)
+        f = lambda v, k: (v >> np.uint64(8 * k)) & np.uint64(0xFF)
+        return np.stack([f(x, 1), f(y, 1), f(x, 3), f(y, 3)], axis=1).astype(np.uint8)
+    m4 = lambda i: ((r0[:, i].astype(np.uint16) + r0[:, i + 1] + r1[:, i] + r1[:, i + 1] + 1) >> 2).astype(np.uint8)
+    assert (perm7351(q[0], q[1]) == np.stack([m4(0), m4(1), m4(2), m4(3)], axis=1)).all()      # DL
+    assert (perm7351(q[1], q[2]) == np.stack([m4(1), m4(2), m4(3), m4(4)], axis=1)).all()      # DR
+
+
+def test_packed_argmin_equals_the_rtl_tree(ob):
+    """K1 replaces find_min_in_10_values (RTL:804-840, a comparison tree) by min(key*16 + rank) with the ranks
+    8,9,4,5,6,7,0,1,2,3 -> 0..9 and the table 0x3210765498: same index for every input, ties included"""
+    L = ob.lib()
+    rank = {8: 0, 9: 1, 4: 2, 5: 3, 6: 4, 7: 5, 0: 6, 1: 7, 2: 8, 3: 9}
+    def packed(v):
+        m = min(v[i] * 16 + rank[i] for i in range(10))
+        return (0x3210765498 >> (4 * (m & 15))) & 15
+    import itertools
+    for v in itertools.product((0, 1, 2), repeat=10):            # every tie pattern over three values
+        assert packed(v) == L.m2v_oracle_find_min10((C.c_int * 10)(*v)), v
+    rng = np.random.default_rng(9)
+    for _ in range(20000):
+        v = [int(x) for x in rng.integers(0, 6, 10)] if rng.random() < 0.5 else [int(x) for x in rng.integers(0, 0x30000, 10)]
+        assert packed(v) == L.m2v_oracle_find_min10((C.c_int * 10)(*v)), v
+
+
+def test_biased_residual_transform_identity():
+    """K1 stages residuals as halfwords biased by +256 and removes 64*8*256 from the first output of the ROW pass: every
+    other row of the RTL's transform matrix (RTL:102-112) sums to zero, so nothing else changes"""
+    Mx = np.array([[64] * 8, [89, 75, 50, 18, -18, -50, -75, -89], [84, 35, -35, -84, -84, -35, 35, 84], [75, -18, -89, -50, 50, 89, 18, -75],
+                   [64, -64, -64, 64, 64, -64, -64, 64], [50, -89, 18, 75, -75, -18, 89, -50], [35, -84, 84, -35, -35, 84, -84, 35],
+                   [18, -50, 75, -89, 89, -75, 50, -18]], dtype=np.int64)
+    assert (Mx[1:].sum(axis=1) == 0).all() and Mx[0].sum() == 512
+    rng = np.random.default_rng(11)
+    R = rng.integers(-255, 256, (2000, 8, 8)).astype(np.int64)
+    rows = (R + 256) @ Mx.T                                       # row pass on the biased halfwords
+    rows[:, :, 0] -= 64 * 8 * 256
+    assert (rows == R @ Mx.T).all()
+    assert (Mx @ rows == Mx @ (R @ Mx.T)).all()
 
 
 def test_index_decode_is_exact():
