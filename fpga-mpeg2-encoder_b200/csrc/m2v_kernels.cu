@@ -71,9 +71,17 @@ __device__ __forceinline__ uint32_t pack4h(uint32_t h0, uint32_t h1) { return __
 #define RBIAS_ROW0 (64 * 8 * 256)
 // mean2 of four byte pairs (RTL:750-757): (a + b + 1) >> 1 == (a | b) - ((a ^ b) >> 1) per byte; the subtraction never borrows
 // across bytes.  One LOP3 less than the compiler's expansion of __vavgu4.
-__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+// The (a ^ b) & mask is one LOP3, spelled in PTX: left to itself the compiler shifts first and masks afterwards, one ALU-pipe
+// instruction more per average.
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {
+    uint32_t t;
+    asm("lop3.b32 %0, %1, %2, 0xFEFEFEFE, 0x28;" : "=r"(t) : "r"(a), "r"(b));
+    return (a | b) - (t >> 1);
+}
 
 // forward 8-point transform with the RTL's 8-bit matrix (RTL:102-112), exact integer butterflies
+// (Measured and rejected: additions written as a * k1 + b with k1 = 1 from the kernel arguments, to keep them off the ALU pipe - the
+// compiler moves other instructions of the region to the ALU pipe instead; 2 ALU instructions less of 315.)
 __device__ __forceinline__ void fdct8(const int x[8], int o[8]) {
     int e0 = x[0] + x[7], e1 = x[1] + x[6], e2 = x[2] + x[5], e3 = x[3] + x[4];
     int d0 = x[0] - x[7], d1 = x[1] - x[6], d2 = x[2] - x[5], d3 = x[3] - x[4];
@@ -177,7 +185,7 @@ static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratc
 
 struct K1Args {
     uint8_t *rec;                                           // reconstruction out: [G][fsz420]
-    int16_t *coefs; uint32_t *mbinfo;
+    int16_t *coefs; uint32_t *mbinfo, *mbchunks;
     int W, H, mbw, mbh, nmb, P, Q, t, CWp;                  // CWp = chroma row stride of the recon buffers (16-byte multiple)
     unsigned fsz420;                                        // bytes per reconstructed frame = W*H + 2*CWp*H/2
     unsigned total;                                         // ngops_t * nmb macroblocks in this launch
@@ -265,9 +273,6 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
             tma_load_4d(smem_u32(S.winC[0]), &tm_refC, cx0, m.by * 8 - 4, 0, m.g, bar);   // one 32x16x2 box: U and V windows
         }
     };
-    // lane-constant parts of the reconstruction store addresses (luma: row lane>>1, 8-byte half lane&1; chroma: lanes 0..15)
-    const unsigned recY_lane = (unsigned)((lane >> 1) * W + 8 * (lane & 1));
-    const unsigned recC_lane = (unsigned)(ysz + (size_t)(((lane >> 3) & 1) * (p.H >> 1) + (lane & 7)) * CWp);
     for (int i = lane; i < 2 * RSTR / 2; i += 32) reinterpret_cast<uint32_t *>(&s.res[6][0])[i] = 0;    // dummy tiles: zero residual,
     for (int i = lane; i < 2 * PSTR / 4; i += 32) reinterpret_cast<uint32_t *>(&s.pred[6][0])[i] = 0;   // zero prediction
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
@@ -510,6 +515,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     //  predicating lanes 16..31 off in the chroma round, or syncing only the lower half-warp with __syncwarp(0xFFFF) held in a
     //  run-time mask - the compiler guards every such sync with MATCH/REDUX/VOTE.)
     int cbp = 0;
+    uint32_t chunkmap = 0;                                       // bit 4*tile + c: the 16-level chunk c of the tile's zig-zag scan holds a level (hint for K2)
     const int Q = p.Q;
 #pragma unroll 1
     for (int round = 0; round < 2; round++) {
@@ -527,6 +533,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         }
         __syncwarp();
         bool nzl = false, maybe = true;
+        uint32_t cm = 0;                                         // chunks this lane wrote a level into
         {                                                        // columns: B = DCTM * A (RTL:2054-2057)
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * TROW + v];
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                             const int C = asr<12>(o[i] + 2048);                      // RTL:2058
                             const int yq = (abs(C) + 2) >> (4 + Q);                  // RTL:2070
                             const int sgn = (C >> 31) | 1;
-                            if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
+                            if (yq) { const uint32_t zz = qt[i * 8 + v].zz; s.res[tile][zz] = (int16_t)(yq * sgn); cm |= 1u << (zz >> 4); nzl = true; }   // zig-zag (RTL:2464)
                             dq = min(yq ? ((2 * yq + 1) << Q) : 0, 2047) * sgn;      // RTL:2134-2137
                         }
                         o[i] = dq;
@@ -585,13 +592,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                     s.res[tile][0] = (int16_t)q;
                     o[0] = 2 * q;
                 }
-                nzl = true;
+                nzl = true; cm = 0xFu;                           // intra tiles: no hint, K2 looks at every chunk
             }
         }
         // cbp bit of this lane's tile (Y00 = 32 ... V = 1; 0 for the dummy tiles 6 and 7): one REDUX.OR gives the coded tiles
         const uint32_t tb = 0x20u >> tile;
         const uint32_t nzm = __reduce_or_sync(FULL, nzl ? tb : 0u);
         cbp |= (int)nzm;
+        chunkmap |= __reduce_or_sync(FULL, cm << (4 * (lane >> 3))) << (16 * round);   // bits 24..31 (round 1, lanes 16..31) belong to the dummies: never read
         // A tile whose levels are all zero reconstructs to exactly the prediction (all-zero input gives
         // (128)>>8 = 0 after the row pass and (8192)>>14 = 0 after the column pass), so its inverse
         // transform is skipped; the decision is per 8-lane group, and when no tile of the round holds a level
@@ -635,10 +643,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         if (p.write_rec) {                                       // warp-uniform: the last frame of a GOP is nobody's reference
             uint8_t *oY = p.rec + (size_t)g * p.fsz420;
             const int y = lane >> 1, half = lane & 1, tile = (y >> 3) * 2 + half;
-            *(uint2 *)(oY + ((unsigned)(Y0 * W + X0) + recY_lane)) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
+            *(uint2 *)(oY + (unsigned)((Y0 + y) * W + X0 + 8 * half)) = *(const uint2 *)&s.pred[tile][(y & 7) * 8];
             if (lane < 16) {
                 const int comp = lane >> 3, cyy = lane & 7;
-                *(uint2 *)(oY + ((unsigned)(by * 8 * CWp + bx * 8) + recC_lane)) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
+                *(uint2 *)(oY + (unsigned)(ysz + (comp * (p.H >> 1) + by * 8 + cyy) * CWp + bx * 8)) = *(const uint2 *)&s.pred[4 + comp][cyy * 8];
             }
         }
         const unsigned mbi = n * (unsigned)p.nmb + mb;           // < 2^25 (m2v_launch_k1 bounds the chunk)
@@ -647,7 +655,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
         for (int k = 0; k < 3; k++)
             if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = *(const uint2 *)&s.res[2 * k + (lane >> 4)][(lane & 15) * 4];
-        if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
+        if (lane == 0) { p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp); p.mbchunks[mbi] = chunkmap; }
     }
     __syncwarp();
     if (!more) break;
@@ -735,7 +743,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st) {
     K1Args a;
     a.rec = b.recon[t & 1];
-    a.coefs = b.coefs; a.mbinfo = b.mbinfo;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mbchunks = b.mbchunks;
     a.W = b.g.W; a.H = b.g.H; a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.Q = b.g.Q; a.t = t;
     a.CWp = b.CWp; a.fsz420 = (unsigned)b.fsz420;
     a.total = (unsigned)(ngops_t * b.g.nmb);
@@ -783,7 +791,7 @@ __device__ __forceinline__ void ac_code(int v, int run, uint32_t &code, int &len
 }
 
 struct K2Args {
-    const int16_t *coefs; const uint32_t *mbinfo;
+    const int16_t *coefs; const uint32_t *mbinfo, *mbchunks;
     uint32_t *mb_bits; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
     uint32_t *out;
     int mbw, mbh, nmb, P; long n0; long total;
@@ -816,7 +824,7 @@ struct BitCount {
 };
 
 template <typename Emit>
-__device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__ zz, int k, uint32_t info, uint32_t li, bool has_left) {
+__device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__ zz, int k, uint32_t info, uint32_t li, bool has_left, uint32_t chunks) {
     const int inter = info & 1, mvx = (int8_t)(info >> 8), mvy = (int8_t)(info >> 16), cbp = (info >> 24) & 63;
     // predictors from the left neighbour; reset at slice start (RTL:2713-2715), DC reset by an inter
     // macroblock (RTL:2786-2792), PMV reset by an intra macroblock (RTL:2771-2773)
@@ -847,8 +855,10 @@ __device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__
         if (!((cbp >> (5 - t)) & 1)) continue;                    // inter tile without a level: nothing (RTL:2799,2804,2828)
         const uint4 *src = (const uint4 *)(zz + t * 64);
         int prevpos = inter ? -1 : 0;                             // the intra DC slot anchors the first run (RTL:2824)
+        const uint32_t cmask = (chunks >> (4 * t)) & 15u;         // K1's hint: 16-level chunks of this tile that hold a level (intra: all four)
 #pragma unroll 1
         for (int ch = 0; ch < 4; ch++) {
+            if (!((cmask >> ch) & 1u)) continue;                  // no level here: not even loaded
             const uint4 a = __ldg(src + 2 * ch), b = __ldg(src + 2 * ch + 1);
             const uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
             // most 16-level chunks of a coded tile are empty (the levels sit at the low frequencies): skip them before
@@ -906,23 +916,24 @@ __global__ void __launch_bounds__(128) k2_vlc(K2Args p) {
     const int k = (int)((p.n0 + f) % (p.P + 1));
     const uint32_t info = __ldg(&p.mbinfo[gw]);
     const uint32_t li = bx > 0 ? __ldg(&p.mbinfo[gw - 1]) : 0u;
+    const uint32_t chunks = __ldg(&p.mbchunks[gw]);
     const int16_t *zz = p.coefs + (size_t)gw * 384;
     if (!WRITE) {
         BitCount bc; bc.n = 0;
-        mb_syntax(bc, zz, k, info, li, bx > 0);
+        mb_syntax(bc, zz, k, info, li, bx > 0, chunks);
         p.mb_bits[gw] = (uint32_t)bc.n;
     } else {
         const int hdr = (k == 0) ? 25 : 18;
         const unsigned long long pos = 8ull * (__ldg(&p.frame_off[f]) + hdr + __ldg(&p.slice_off[f * p.mbh + by])) + __ldg(&p.mb_off[gw]);
         BitAcc bw; bw.start(p.out, pos);
-        mb_syntax(bw, zz, k, info, li, bx > 0);
+        mb_syntax(bw, zz, k, info, li, bx > 0, chunks);
         bw.flush();
     }
 }
 
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
     K2Args a;
-    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mbchunks = b.mbchunks; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
     a.frame_off = b.frame_off; a.out = b.out_words;
     a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
     a.F = b.F; a.cap_words = b.out_cap_words;
