@@ -235,6 +235,7 @@ def main():
     ap.add_argument('--frames', type=int, default=0, help='frames per GPU (config 5: total frames); 0 = config default')
     ap.add_argument('--q', type=int, default=2, help='Q_LEVEL 1..4')
     ap.add_argument('--chunks', type=int, default=2, help='chunks per rank and step of the to-host pipeline')
+    ap.add_argument('--tail-gops', type=int, default=8, help='GOPs of the last (small) chunk of the to-host pipeline: only its copy to the host is exposed')
     ap.add_argument('--e2e-frames', type=int, default=256)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
@@ -368,7 +369,7 @@ def main():
     blockcyclic = cfg['scaling'] == 'weak'
     nrow = max(1, a.chunks if blockcyclic else min(a.chunks, 2))
     if blockcyclic:
-        sched = sharding.chunk_schedule(F, P, world, nrow)[rank]
+        sched = sharding.chunk_schedule(F, P, world, nrow, a.tail_gops)[rank]
     else:
         sched = [(f0, k, n0 + f0) for (f0, k, _) in sharding.chunk_schedule(F, P, 1, nrow)[0]] if F else []
     arena_bytes = int(total_frames * W * H * max(0.25, 2.0 * body_len / max(F * W * H, 1))) + (1 << 20)
@@ -514,9 +515,10 @@ def main():
     e2e = None
     if not a.no_e2e and F:
         Fe = max(gop, min(a.e2e_frames // gop * gop, F))
-        host = torch.empty((Fe, 3, H, W), dtype=torch.uint8).pin_memory()
+        pin = pkg.PinnedArray(Fe * fsz)                          # m2v_alloc_host: pinned, and seen as pinned by every device of the process
+        host = torch.from_numpy(pin.array).view(Fe, 3, H, W)
         host.copy_(frames[:Fe])
-        hnp = host.numpy()
+        hnp = pin.array.reshape(Fe, 3, H, W)
         e2 = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q)
         sink = np.empty(64 << 20, np.uint8)                      # the caller's stream buffer (m2v_drain copies the words into it)
         def one(e=e2, src=hnp):
@@ -563,8 +565,8 @@ def main():
 
         # ---- E. the same stream through ONE process and ONE handle over all GPUs (m2v_create_multi), rank 0 ----
         if world > 1 and not a.no_extras:
-            barrier()
-            if rank == 0:
+            barrier()                                             # the other ranks then wait on the HOST (arena flag): a rank parked in an NCCL
+            if rank == 0:                                         # barrier keeps a kernel spinning on its GPU, which this handle also drives
                 try:
                     em = pkg.Mpeg2Encoder(XL=7, YL=7, VECTOR_LEVEL=VL, Q_LEVEL=a.q, ndev=world)
                     for _ in range(2):
@@ -580,6 +582,7 @@ def main():
                                         'api': 'm2v_create_multi(%d) + m2v_begin / m2v_push_frames / m2v_stop / m2v_drain from ONE host thread; the other ranks idle' % world}
                 except Exception as ex:
                     e2e['e2e_multi'] = {'error': str(ex)[:200]}
+            bar[0] += 1; arena.barrier(bar[0], sleep=0.002 if rank else 0.0)
             barrier()
 
         # ---- F. file -> file with the C++ testbench replay (N=1) ----
@@ -604,13 +607,14 @@ def main():
                                        'frac_of_e2e': round(modes[best]['value'] / e2e['value'], 4) if best else None,
                                        'stream_equals_e2e': bool(all(m['stream_equals_e2e'] for m in modes.values())), 'dir': d,
                                        'read_ahead_alone_mpixel_s': dry[-1] if dry else None,
-                                       'api': 'csrc/m2venc_tb: copy = read-ahead into a ring of pinned chunks (8 pread threads) -> m2v_push_frames -> m2v_drain -> write-behind; '
+                                       'api': 'csrc/m2venc_tb: copy = read-ahead into a ring of pinned chunks (up to 16 pread threads) -> m2v_push_frames -> m2v_drain -> write-behind; '
                                               'pin = the mapped file pinned in place chunk by chunk, no copy; second of two passes over the same file on one handle'}
                 for f in (fin, fout):
                     os.unlink(f)
             except Exception as ex:
                 e2e['file_to_file'] = {'error': str(ex)[:200]}
-        del host
+        del host, hnp
+        pin.close()
 
     # ---- G. real picture content (the reference's own clip, where it travelled) ----
     real = None
@@ -701,7 +705,7 @@ def main():
             'dtype': 'u8', 'data': 'synthetic', 'config': config, 'fps': round(value * 1e6 / (W * H), 1),
             'wall_ms_per_step': round(wall_ms_per_step, 3), 'stream_bytes': total_stream,
             'bytes_per_pixel_out': round(body_len / max(F * W * H, 1), 5),
-            'value_to_host': {'value': round(value_to_host, 2), 'unit': 'Mpixel/s', 'ms_per_step': round(th_ms, 3), 'chunks_per_rank': len(sched),
+            'value_to_host': {'value': round(value_to_host, 2), 'unit': 'Mpixel/s', 'ms_per_step': round(th_ms, 3), 'chunks_per_rank': len(sched), 'chunk_frames': [k for (_, k, _) in sched],
                               'gpu_launches': launches_to_host, 'fps': round(value_to_host * 1e6 / (W * H), 1),
                               'protocol': 'SURVEY 8(d): inputs resident in HBM; first launch -> last byte of the concatenated stream of all ranks in rank 0\'s host memory; '
                                           'host clock between two barriers, max over ranks',

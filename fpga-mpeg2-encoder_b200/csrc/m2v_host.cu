@@ -17,7 +17,9 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
+#include <stdlib.h>
 #include <deque>
 #include <mutex>
 #include <new>
@@ -28,6 +30,14 @@
 #include <vector>
 
 namespace {
+
+// M2V_TRACE=1 in the environment: the workers print a timestamped line per pipeline event (stderr)
+static const bool g_trace = getenv("M2V_TRACE") != nullptr;
+static double now_ms() {
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+#define TRACE(dev, ...) do { if (g_trace) { fprintf(stderr, "[m2v dev%d %10.3f ms] ", dev, now_ms()); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
 
 struct Range {                                    // NVTX range around the host side of a phase (enqueue / wait)
     explicit Range(const char *name) { nvtxRangePushA(name); }
@@ -72,7 +82,7 @@ struct DevCtx {
     DevBuf<uint8_t> d_in[2], d_recon0, d_recon1, d_body;
     DevBuf<uint4> d_out[2];
     DevBuf<int16_t> d_coefs;
-    DevBuf<uint32_t> d_mbinfo, d_mbchunks, d_mb_bits, d_mb_off, d_slice_off, d_frame_bytes;
+    DevBuf<uint32_t> d_mbinfo, d_mb_bits, d_mb_off, d_slice_off, d_frame_bytes;
     DevBuf<unsigned long long> d_frame_off;
     DevBuf<unsigned> d_k1ctr; unsigned k1_seq = 0;
     unsigned long long *h_total = nullptr;                              // pinned [2]: body bytes of the batch in each slot
@@ -124,7 +134,7 @@ void ctx_destroy(DevCtx &c) {
     for (int k = 0; k < 2; k++) for (int i = 0; i < 5; i++) if (c.ev_t[k][i]) cudaEventDestroy(c.ev_t[k][i]);
     for (int i = 0; i < 2; i++) { c.d_in[i].release(); c.d_out[i].release(); }
     c.d_recon0.release(); c.d_recon1.release(); c.d_body.release(); c.d_coefs.release();
-    c.d_mbinfo.release(); c.d_mbchunks.release(); c.d_mb_bits.release(); c.d_mb_off.release(); c.d_slice_off.release();
+    c.d_mbinfo.release(); c.d_mb_bits.release(); c.d_mb_off.release(); c.d_slice_off.release();
     c.d_frame_bytes.release(); c.d_frame_off.release(); c.d_k1ctr.release();
     if (c.h_total) cudaFreeHost(c.h_total);
     c.h_total = nullptr;
@@ -142,11 +152,11 @@ int encode_enqueue(DevCtx &c, const Geom &g, const uint8_t *d_in, long F, long n
     const size_t fsz420 = b.fsz420, nmbF = (size_t)F * b.g.nmb;
     if (G * b.g.nmb >= M2V_K1_MAX_MBS) { snprintf(c.err, sizeof c.err, "chunk too large for one K1 launch"); return M2V_EINVAL; }
     CKC(c.d_recon0.reserve(G * fsz420)); CKC(c.d_recon1.reserve(g.P ? G * fsz420 : 16));
-    CKC(c.d_coefs.reserve(nmbF * 384)); CKC(c.d_mbinfo.reserve(nmbF)); CKC(c.d_mbchunks.reserve(nmbF)); CKC(c.d_mb_bits.reserve(nmbF)); CKC(c.d_mb_off.reserve(nmbF));
+    CKC(c.d_coefs.reserve(nmbF * 384)); CKC(c.d_mbinfo.reserve(nmbF)); CKC(c.d_mb_bits.reserve(nmbF)); CKC(c.d_mb_off.reserve(nmbF));
     CKC(c.d_slice_off.reserve((size_t)F * g.mbh)); CKC(c.d_frame_bytes.reserve(F)); CKC(c.d_frame_off.reserve(F + 1));
     CKC(c.d_out[slot].reserve((nmbF * c.reserve_per_mb + 15) / 16 + 4));
     b.recon[0] = c.d_recon0.p; b.recon[1] = g.P ? c.d_recon1.p : c.d_recon0.p;
-    b.coefs = c.d_coefs.p; b.mbinfo = c.d_mbinfo.p; b.mbchunks = c.d_mbchunks.p; b.mb_bits = c.d_mb_bits.p; b.mb_off = c.d_mb_off.p;
+    b.coefs = c.d_coefs.p; b.mbinfo = c.d_mbinfo.p; b.mb_bits = c.d_mb_bits.p; b.mb_off = c.d_mb_off.p;
     b.slice_off = c.d_slice_off.p; b.frame_bytes = c.d_frame_bytes.p; b.frame_off = c.d_frame_off.p;
     b.out_words = (uint32_t *)c.d_out[slot].p; b.out_cap_words = c.d_out[slot].n * 4;
     b.k1_ctr = c.d_k1ctr.p; b.k1_grid_cap_i = c.grid_cap_i; b.k1_grid_cap_p = c.grid_cap_p;
@@ -297,6 +307,7 @@ void worker_main(m2v_encoder *e, Worker *w) {
         size_t len = 0;
         int rc;
         { Range r("m2v wait size"); rc = encode_size(c, p.slot, &len); }
+        TRACE(c.dev, "batch n0=%ld: scans done, body %zu bytes", p.j.n0, len);
         PinBuf *buf = nullptr;
         if (!rc) {
             std::lock_guard<std::mutex> lk(e->mu);
@@ -311,6 +322,7 @@ void worker_main(m2v_encoder *e, Worker *w) {
             if (ce == cudaSuccess) ce = cudaEventSynchronize(c.ev_out[p.slot]);
             if (ce != cudaSuccess) { snprintf(c.err, sizeof c.err, "device->host copy of a body: %s", cudaGetErrorString(ce)); rc = M2V_ECUDA; }
         }
+        TRACE(c.dev, "batch n0=%ld: body in host memory", p.j.n0);
         std::lock_guard<std::mutex> lk(e->mu);
         Seg &s = e->segs[p.j.seg - e->seg_base];
         if (rc) { fail_async(e, rc, c.err[0] ? c.err : "worker failed"); if (buf) e->pool.push_back(buf); s.len = 0; }
@@ -325,6 +337,7 @@ void worker_main(m2v_encoder *e, Worker *w) {
         if (!x.valid) return;
         x.valid = false;
         cudaError_t ce = cudaEventSynchronize(c.ev_in[x.slot]);
+        TRACE(c.dev, "batch n0=%ld: host->device copy done", x.j.n0);
         if (ce != cudaSuccess && !x.rc) { snprintf(c.err, sizeof c.err, "host->device copy of a batch: %s", cudaGetErrorString(ce)); x.rc = M2V_ECUDA; }
         std::lock_guard<std::mutex> lk(e->mu);
         if (x.j.stage >= 0) e->stage_busy[x.j.stage] = false;
@@ -351,6 +364,7 @@ void worker_main(m2v_encoder *e, Worker *w) {
         }
         const int slot = (int)(k++ & 1);
         const size_t fsz = (size_t)j.g.mbw * j.g.mbh * 768, bytes = fsz * j.nframes;
+        TRACE(c.dev, "batch n0=%ld: %ld frames, %zu bytes, slot %d: queueing copy and kernels", j.n0, j.nframes, bytes, slot);
         int rc = M2V_OK;
         {
             // d_in[slot] and d_out[slot] were last used by batch k-2, which finalize() saw through to its device->host copy
@@ -362,6 +376,7 @@ void worker_main(m2v_encoder *e, Worker *w) {
             if (ce != cudaSuccess) { snprintf(c.err, sizeof c.err, "host->device copy of a batch: %s", cudaGetErrorString(ce)); rc = M2V_ECUDA; }
         }
         if (!rc) rc = encode_enqueue(c, j.g, c.d_in[slot].p, j.nframes, j.n0, slot);
+        TRACE(c.dev, "batch n0=%ld: queued", j.n0);
         // batch k's copy and kernels are queued: now the previous batch's copy-done signal and its way out
         complete_copy(cw);
         finalize(pend);

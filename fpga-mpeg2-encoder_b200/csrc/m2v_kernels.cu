@@ -185,7 +185,7 @@ static_assert(4 * TSTR * 4 <= sizeof(uint32_t) * (2 * 16 * 8 + 32 * 12), "scratc
 
 struct K1Args {
     uint8_t *rec;                                           // reconstruction out: [G][fsz420]
-    int16_t *coefs; uint32_t *mbinfo, *mbchunks;
+    int16_t *coefs; uint32_t *mbinfo;
     int W, H, mbw, mbh, nmb, P, Q, t, CWp;                  // CWp = chroma row stride of the recon buffers (16-byte multiple)
     unsigned fsz420;                                        // bytes per reconstructed frame = W*H + 2*CWp*H/2
     unsigned total;                                         // ngops_t * nmb macroblocks in this launch
@@ -209,6 +209,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (spins > (1u << 24)) __trap();
     }
+}
+// one lane of the (converged) warp, chosen by the hardware: the form the compiler turns into a single ELECT and a uniform branch
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     const MbPos nxt = decode(nidx);
     unsigned drawn = 0;
     if (more) {
-        if (lane == 0) { fence_proxy_async(); issue(nxt, stg ^ 1); }
+        if (elect_one()) { fence_proxy_async(); issue(nxt, stg ^ 1); }
         drawn = draw();
     }
     const int g = cur.g, by = cur.by, bx = cur.bx;
@@ -368,9 +374,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
                 for (int dyi = R + 1; dyi <= 2 * R; dyi++) fold(dyi);
             }
-            const int dx = lane - R;
-            best += (uint32_t)(2 * R - lane);                // R - dx; only lanes 0..2R (half 0, one per dx) take part below
-            if (lane > 2 * R || (bx == 0 && dx < 0) || (bx == p.mbw - 1 && dx > 0)) best = 0xFFFFFFFFu;
+            best += (uint32_t)(2 * R - lane);                // R - dx, dx = lane - R; only lanes 0..2R (half 0, one per dx) take part below
+            // lanes lo..hi are allowed: dx < 0 is forbidden in the first block column, dx > 0 in the last (warp-uniform bounds)
+            const unsigned lo = bx == 0 ? R : 0, hi = bx == p.mbw - 1 ? R : 2 * R;
+            if ((unsigned)lane - lo > hi - lo) best = 0xFFFFFFFFu;
             best = __reduce_min_sync(FULL, best);
             if (best < (1u << 22)) { fmvy = R - (int)((best >> 5) & 31); fmvx = R - (int)(best & 31); }
         }
@@ -515,7 +522,6 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     //  predicating lanes 16..31 off in the chroma round, or syncing only the lower half-warp with __syncwarp(0xFFFF) held in a
     //  run-time mask - the compiler guards every such sync with MATCH/REDUX/VOTE.)
     int cbp = 0;
-    uint32_t chunkmap = 0;                                       // bit 4*tile + c: the 16-level chunk c of the tile's zig-zag scan holds a level (hint for K2)
     const int Q = p.Q;
 #pragma unroll 1
     for (int round = 0; round < 2; round++) {
@@ -533,7 +539,6 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         }
         __syncwarp();
         bool nzl = false, maybe = true;
-        uint32_t cm = 0;                                         // chunks this lane wrote a level into
         {                                                        // columns: B = DCTM * A (RTL:2054-2057)
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = tt[k * TROW + v];
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                             const int C = asr<12>(o[i] + 2048);                      // RTL:2058
                             const int yq = (abs(C) + 2) >> (4 + Q);                  // RTL:2070
                             const int sgn = (C >> 31) | 1;
-                            if (yq) { const uint32_t zz = qt[i * 8 + v].zz; s.res[tile][zz] = (int16_t)(yq * sgn); cm |= 1u << (zz >> 4); nzl = true; }   // zig-zag (RTL:2464)
+                            if (yq) { s.res[tile][qt[i * 8 + v].zz] = (int16_t)(yq * sgn); nzl = true; }   // zig-zag (RTL:2464)
                             dq = min(yq ? ((2 * yq + 1) << Q) : 0, 2047) * sgn;      // RTL:2134-2137
                         }
                         o[i] = dq;
@@ -592,14 +597,15 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
                     s.res[tile][0] = (int16_t)q;
                     o[0] = 2 * q;
                 }
-                nzl = true; cm = 0xFu;                           // intra tiles: no hint, K2 looks at every chunk
+                nzl = true;
             }
         }
         // cbp bit of this lane's tile (Y00 = 32 ... V = 1; 0 for the dummy tiles 6 and 7): one REDUX.OR gives the coded tiles
         const uint32_t tb = 0x20u >> tile;
         const uint32_t nzm = __reduce_or_sync(FULL, nzl ? tb : 0u);
         cbp |= (int)nzm;
-        chunkmap |= __reduce_or_sync(FULL, cm << (4 * (lane >> 3))) << (16 * round);   // bits 24..31 (round 1, lanes 16..31) belong to the dummies: never read
+        // (Measured and rejected: a second REDUX.OR collecting, per tile, which 16-level chunks of the zig-zag scan hold a level, so that
+        //  K2 loads only those: K2 -0.03 ms of 0.81, K1 +0.19 ms of 8.25 per step - K2's own all-zero test of a loaded chunk is as good.)
         // A tile whose levels are all zero reconstructs to exactly the prediction (all-zero input gives
         // (128)>>8 = 0 after the row pass and (8192)>>14 = 0 after the column pass), so its inverse
         // transform is skipped; the decision is per 8-lane group, and when no tile of the round holds a level
@@ -655,7 +661,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
         for (int k = 0; k < 3; k++)
             if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = *(const uint2 *)&s.res[2 * k + (lane >> 4)][(lane & 15) * 4];
-        if (lane == 0) { p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp); p.mbchunks[mbi] = chunkmap; }
+        if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
     }
     __syncwarp();
     if (!more) break;
@@ -743,7 +749,7 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st) {
     K1Args a;
     a.rec = b.recon[t & 1];
-    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mbchunks = b.mbchunks;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo;
     a.W = b.g.W; a.H = b.g.H; a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.Q = b.g.Q; a.t = t;
     a.CWp = b.CWp; a.fsz420 = (unsigned)b.fsz420;
     a.total = (unsigned)(ngops_t * b.g.nmb);
@@ -791,7 +797,7 @@ __device__ __forceinline__ void ac_code(int v, int run, uint32_t &code, int &len
 }
 
 struct K2Args {
-    const int16_t *coefs; const uint32_t *mbinfo, *mbchunks;
+    const int16_t *coefs; const uint32_t *mbinfo;
     uint32_t *mb_bits; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
     uint32_t *out;
     int mbw, mbh, nmb, P; long n0; long total;
@@ -824,7 +830,7 @@ struct BitCount {
 };
 
 template <typename Emit>
-__device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__ zz, int k, uint32_t info, uint32_t li, bool has_left, uint32_t chunks) {
+__device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__ zz, int k, uint32_t info, uint32_t li, bool has_left) {
     const int inter = info & 1, mvx = (int8_t)(info >> 8), mvy = (int8_t)(info >> 16), cbp = (info >> 24) & 63;
     // predictors from the left neighbour; reset at slice start (RTL:2713-2715), DC reset by an inter
     // macroblock (RTL:2786-2792), PMV reset by an intra macroblock (RTL:2771-2773)
@@ -855,10 +861,8 @@ __device__ __forceinline__ void mb_syntax(Emit &out, const int16_t *__restrict__
         if (!((cbp >> (5 - t)) & 1)) continue;                    // inter tile without a level: nothing (RTL:2799,2804,2828)
         const uint4 *src = (const uint4 *)(zz + t * 64);
         int prevpos = inter ? -1 : 0;                             // the intra DC slot anchors the first run (RTL:2824)
-        const uint32_t cmask = (chunks >> (4 * t)) & 15u;         // K1's hint: 16-level chunks of this tile that hold a level (intra: all four)
 #pragma unroll 1
         for (int ch = 0; ch < 4; ch++) {
-            if (!((cmask >> ch) & 1u)) continue;                  // no level here: not even loaded
             const uint4 a = __ldg(src + 2 * ch), b = __ldg(src + 2 * ch + 1);
             const uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
             // most 16-level chunks of a coded tile are empty (the levels sit at the low frequencies): skip them before
@@ -916,24 +920,23 @@ __global__ void __launch_bounds__(128) k2_vlc(K2Args p) {
     const int k = (int)((p.n0 + f) % (p.P + 1));
     const uint32_t info = __ldg(&p.mbinfo[gw]);
     const uint32_t li = bx > 0 ? __ldg(&p.mbinfo[gw - 1]) : 0u;
-    const uint32_t chunks = __ldg(&p.mbchunks[gw]);
     const int16_t *zz = p.coefs + (size_t)gw * 384;
     if (!WRITE) {
         BitCount bc; bc.n = 0;
-        mb_syntax(bc, zz, k, info, li, bx > 0, chunks);
+        mb_syntax(bc, zz, k, info, li, bx > 0);
         p.mb_bits[gw] = (uint32_t)bc.n;
     } else {
         const int hdr = (k == 0) ? 25 : 18;
         const unsigned long long pos = 8ull * (__ldg(&p.frame_off[f]) + hdr + __ldg(&p.slice_off[f * p.mbh + by])) + __ldg(&p.mb_off[gw]);
         BitAcc bw; bw.start(p.out, pos);
-        mb_syntax(bw, zz, k, info, li, bx > 0, chunks);
+        mb_syntax(bw, zz, k, info, li, bx > 0);
         bw.flush();
     }
 }
 
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
     K2Args a;
-    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mbchunks = b.mbchunks; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
     a.frame_off = b.frame_off; a.out = b.out_words;
     a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
     a.F = b.F; a.cap_words = b.out_cap_words;

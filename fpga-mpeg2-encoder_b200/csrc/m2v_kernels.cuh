@@ -26,7 +26,6 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     CUtensorMap tm_in, tm_refY[2], tm_refC[2];   // TMA descriptors (m2v_make_tmaps)
     int16_t *coefs;            // [F][nmb][6][64] quantised levels, zig-zag order
     uint32_t *mbinfo;          // [F][nmb]
-    uint32_t *mbchunks;        // [F][nmb]  bit 4*tile + c: 16-level chunk c of the tile's zig-zag scan holds a level (K1's hint for K2)
     uint32_t *mb_bits;         // [F][nmb]  bit length of each macroblock's syntax
     uint32_t *mb_off;          // [F][nmb]  bit offset inside its slice (slice header included)
     uint32_t *slice_off;       // [F][mbh]  byte offset of slice inside the frame's slice area

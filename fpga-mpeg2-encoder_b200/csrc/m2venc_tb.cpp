@@ -14,7 +14,7 @@
 // defaults = testbench defaults: XL=7 YL=6 VECTOR_LEVEL=3 Q_LEVEL=2 i_pframes_count=23 (TB:23-24,98-99,106)
 //   -gpus n   one module instance spread over n GPUs (m2v_create_multi)
 //   -push4    the 4-pixel port, one call per "clock";  -frame   one frame per push (the testbench's frame loop)
-//   -chunk n  frames per read-ahead chunk (default: whole GOPs, ~256 MiB);  -readers n  threads per chunk (default 8)
+//   -chunk n  frames per read-ahead chunk (default: whole GOPs, ~256 MiB);  -readers n  threads per chunk (default: 2/3 of the hardware threads, 4..16)
 //   -pin      no copy at all: the file is mapped and each chunk of the mapping is pinned in place (m2v_register_host) by the
 //             read-ahead thread, pushed from there and unpinned (falls back to the copying ring where pinning is refused)
 //   -dry      read ahead only, nothing is pushed: prints what the input side alone delivers
@@ -140,7 +140,9 @@ struct WriteBehind {
 }  // namespace
 
 int main(int argc, char **argv) {
-    int XL = 7, YL = 6, VL = 3, Q = 2, P = 23, push4 = 0, per_frame = 0, gpus = 1, readers = 8, pin = 0, dry = 0, i = 1;
+    int XL = 7, YL = 6, VL = 3, Q = 2, P = 23, push4 = 0, per_frame = 0, gpus = 1, pin = 0, dry = 0, i = 1;
+    // reading a file is a CPU copy out of the page cache: ~3 GB/s per thread; two thirds of the hardware threads, 4..16
+    int readers = (int)std::min(16u, std::max(4u, std::thread::hardware_concurrency() * 2 / 3));
     long chunk_opt = 0;
     for (; i < argc && argv[i][0] == '-'; i++) {
         std::string a = argv[i];

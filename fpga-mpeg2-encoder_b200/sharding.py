@@ -35,16 +35,21 @@ def gop_partition(nframes, pframes_count, world):
     return out
 
 
-def chunk_schedule(frames_per_rank, pframes_count, world, chunks):
+def chunk_schedule(frames_per_rank, pframes_count, world, chunks, tail_gops=0):
     """Block-cyclic deal of one long sequence for the pipelined gather: the sequence is cut into `chunks * world` blocks of
     whole GOPs and block c*world + r goes to rank r as its chunk c.  All bodies of chunk row c are known (and on their way
-    to the host) while the ranks encode chunk row c+1.  Returns per rank the list of (first local frame, frames, absolute
-    index of the first frame)."""
+    to the host) while the ranks encode chunk row c+1, so only the LAST row's device->host copy is exposed: with
+    tail_gops > 0 (and chunks > 1) that last chunk is made small (tail_gops GOPs) and the others share the rest.
+    Returns per rank the list of (first local frame, frames, absolute index of the first frame)."""
     gop = pframes_count + 1
     gops = frames_per_rank // gop
     chunks = max(1, min(chunks, gops))
-    base, extra = divmod(gops, chunks)
-    per = [(base + (1 if c < extra else 0)) * gop for c in range(chunks)]
+    if tail_gops > 0 and chunks > 1 and gops > tail_gops + (chunks - 2):
+        base, extra = divmod(gops - tail_gops, chunks - 1)
+        per = [(base + (1 if c < extra else 0)) * gop for c in range(chunks - 1)] + [tail_gops * gop]
+    else:
+        base, extra = divmod(gops, chunks)
+        per = [(base + (1 if c < extra else 0)) * gop for c in range(chunks)]
     out = [[] for _ in range(world)]
     n_abs = 0
     for c in range(chunks):
@@ -99,8 +104,8 @@ class HostArena:
     know where my body goes"."""
     TABLE = 1 << 16
 
-    def __init__(self, pkg, name, nbytes, rank, world, rows=64):
-        self.pkg, self.rank, self.world, self.rows = pkg, rank, world, rows
+    def __init__(self, pkg, name, nbytes, rank, world, rows=64, pin=True):
+        self.pkg, self.rank, self.world, self.rows, self.pinned = pkg, rank, world, rows, pin
         self.path = '/dev/shm/' + name
         self.nbytes = self.TABLE + nbytes
         assert rows * world * 16 + world * 16 <= self.TABLE
@@ -114,11 +119,10 @@ class HostArena:
         os.close(fd)
         self.buf = np.frombuffer(self.mm, dtype=np.uint8)
         self.addr = self.buf.ctypes.data
-        if rank == 0:
-            self.buf[:] = 0                                        # touch the pages once, before they are pinned
-        rc = pkg.lib().m2v_register_host(self.addr, self.nbytes)
-        if rc:
-            raise pkg.M2VError(rc, 'm2v_register_host(host arena)')
+        if pin:                                                   # pin=False: host-only use (the CPU tests of the table and the barrier)
+            rc = pkg.lib().m2v_register_host(self.addr, self.nbytes)
+            if rc:
+                raise pkg.M2VError(rc, 'm2v_register_host(host arena)')
         self.table = self.buf[:rows * world * 16].view(np.int64).reshape(rows, world, 2)
         self.flags = self.buf[rows * world * 16:rows * world * 16 + world * 16].view(np.int64).reshape(world, 2)
         self.stream = self.buf[self.TABLE:]
@@ -137,18 +141,21 @@ class HostArena:
                 raise TimeoutError('host arena: a rank did not publish row %d epoch %d' % (row, epoch))
         return t[:, 1].copy()
 
-    def barrier(self, epoch, timeout=60.0):
-        """all ranks have reached `epoch` (monotonically increasing)"""
+    def barrier(self, epoch, timeout=120.0, sleep=0.0):
+        """all ranks have reached `epoch` (monotonically increasing); sleep > 0 polls instead of spinning (long waits)"""
         self.flags[self.rank, 0] = epoch
         t0 = time.perf_counter()
         while not bool((self.flags[:, 0] >= epoch).all()):
+            if sleep:
+                time.sleep(sleep)
             if time.perf_counter() - t0 > timeout:
                 raise TimeoutError('host arena: barrier %d' % epoch)
 
     def close(self):
         if getattr(self, 'mm', None) is None:
             return
-        self.pkg.lib().m2v_unregister_host(self.addr)
+        if self.pinned:
+            self.pkg.lib().m2v_unregister_host(self.addr)
         self.table = self.flags = self.stream = self.buf = None
         try:
             self.mm.close()

@@ -214,6 +214,77 @@ def test_two_rank_gloo_gather(tmp_path):
     assert 'OK' in outs[0]
 
 
+def test_chunk_schedule_covers_the_sequence_in_order(pkg):
+    """block-cyclic deal for the pipelined gather: every frame exactly once, absolute indices in stream order (chunk row, then
+    rank), whole GOPs, local ranges contiguous per rank; with a small tail chunk the last row is the short one"""
+    from fpga_mpeg2_encoder_b200 import sharding
+    for (F, P, world, chunks, tail) in ((512, 15, 1, 2, 0), (512, 15, 8, 2, 8), (512, 15, 4, 3, 2), (96, 7, 2, 5, 1), (16, 15, 2, 4, 0), (40, 3, 3, 2, 9)):
+        gop = P + 1
+        sched = sharding.chunk_schedule(F, P, world, chunks, tail)
+        assert len(sched) == world and len({len(s) for s in sched}) == 1
+        nabs = 0
+        for c in range(len(sched[0])):
+            for r in range(world):
+                f0, k, a0 = sched[r][c]
+                assert k % gop == 0 and k > 0 and a0 == nabs and a0 % gop == 0
+                assert f0 == sum(x[1] for x in sched[r][:c])
+                nabs += k
+        assert nabs == world * (F // gop) * gop
+        if tail and len(sched[0]) > 1 and F // gop > tail + len(sched[0]) - 2:
+            assert sched[0][-1][1] == tail * gop
+
+
+_ARENA_WORKER = r'''
+import sys, os
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np
+import __graft_entry__ as ge
+pkg = ge.load_package()
+from fpga_mpeg2_encoder_b200 import sharding
+rank, world, name = int(sys.argv[1]), 3, sys.argv[2]
+arena = sharding.HostArena(pkg, name, 1 << 16, rank, world, pin=False)
+arena.barrier(1)
+base = 34
+for step in range(3):
+    for c in range(4):
+        epoch = step * 4 + c + 1
+        nb = 100 * (rank + 1) + 10 * c + step
+        arena.publish(c, epoch, nb)
+        sz = arena.sizes(c, epoch)
+        assert list(sz) == [100 * (r + 1) + 10 * c + step for r in range(world)], (rank, step, c, sz)
+        off = base + int(sz[:rank].sum())
+        arena.stream[off:off + nb] = rank + 1                    # every rank writes its "body" at its final offset
+        base += int(sz.sum())
+    arena.barrier(step + 2)
+    if rank == 0:
+        got = arena.stream[34:base]
+        want = np.concatenate([np.full(100 * (r + 1) + 10 * c + step, r + 1, np.uint8) for c in range(4) for r in range(world)])
+        assert (got == want).all()
+        print('ARENA OK', step, flush=True)
+    arena.barrier(100 + step)
+    base = 34
+arena.close()
+'''
+
+
+def test_host_arena_three_processes(tmp_path):
+    """sharding.HostArena without a GPU (pin=False): three processes publish sizes through the shared table, write their
+    bodies at the offsets they derive, and rank 0 finds the concatenation in order - three steps, so that the epochs separate them"""
+    name = 'm2v_cpu_test_%d' % os.getpid()
+    script = tmp_path / 'arena_worker.py'
+    script.write_text(_ARENA_WORKER.format(root=ROOT))
+    p0 = subprocess.Popen([sys.executable, str(script), '0', name], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    import time
+    for _ in range(600):
+        if os.path.exists('/dev/shm/' + name) and os.path.getsize('/dev/shm/' + name) == (1 << 16) + (1 << 16):
+            break
+        time.sleep(0.05)
+    ps = [p0] + [subprocess.Popen([sys.executable, str(script), str(r), name], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in (1, 2)]
+    outs = [p.communicate(timeout=240)[0] for p in ps]
+    assert all(p.returncode == 0 for p in ps), outs
+    assert outs[0].count('ARENA OK') == 3
+
+
 def test_synth_is_deterministic(synth):
     for name, gen in synth.GENERATORS.items():
         a = gen(42, 3, 64, 48); b = gen(42, 3, 64, 48)

@@ -15,8 +15,9 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, 'fpga-mpeg2-encoder_b200', 'csrc', 'm2v_kernels.cu')
-LIB = os.path.join(ROOT, 'fpga-mpeg2-encoder_b200', 'libm2venc.so')
+# the capture must be read with the library (and source) it was taken from: M2V_LIB / M2V_SRC point at an older build
+SRC = os.environ.get('M2V_SRC', os.path.join(ROOT, 'fpga-mpeg2-encoder_b200', 'csrc', 'm2v_kernels.cu'))
+LIB = os.environ.get('M2V_LIB', os.path.join(ROOT, 'fpga-mpeg2-encoder_b200', 'libm2venc.so'))
 METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem',
            'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
            'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
