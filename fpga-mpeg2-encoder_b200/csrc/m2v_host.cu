@@ -82,7 +82,7 @@ struct DevCtx {
     DevBuf<uint8_t> d_in[2], d_recon0, d_recon1, d_body;
     DevBuf<uint4> d_out[2];
     DevBuf<int16_t> d_coefs;
-    DevBuf<uint32_t> d_mbinfo, d_mb_bits, d_mb_off, d_slice_off, d_frame_bytes;
+    DevBuf<uint32_t> d_mbinfo, d_mb_bits, d_mb_code, d_mb_off, d_slice_off, d_frame_bytes;
     DevBuf<unsigned long long> d_frame_off;
     DevBuf<unsigned> d_k1ctr; unsigned k1_seq = 0;
     unsigned long long *h_total = nullptr;                              // pinned [2]: body bytes of the batch in each slot
@@ -134,7 +134,7 @@ void ctx_destroy(DevCtx &c) {
     for (int k = 0; k < 2; k++) for (int i = 0; i < 5; i++) if (c.ev_t[k][i]) cudaEventDestroy(c.ev_t[k][i]);
     for (int i = 0; i < 2; i++) { c.d_in[i].release(); c.d_out[i].release(); }
     c.d_recon0.release(); c.d_recon1.release(); c.d_body.release(); c.d_coefs.release();
-    c.d_mbinfo.release(); c.d_mb_bits.release(); c.d_mb_off.release(); c.d_slice_off.release();
+    c.d_mbinfo.release(); c.d_mb_bits.release(); c.d_mb_code.release(); c.d_mb_off.release(); c.d_slice_off.release();
     c.d_frame_bytes.release(); c.d_frame_off.release(); c.d_k1ctr.release();
     if (c.h_total) cudaFreeHost(c.h_total);
     c.h_total = nullptr;
@@ -152,11 +152,11 @@ int encode_enqueue(DevCtx &c, const Geom &g, const uint8_t *d_in, long F, long n
     const size_t fsz420 = b.fsz420, nmbF = (size_t)F * b.g.nmb;
     if (G * b.g.nmb >= M2V_K1_MAX_MBS) { snprintf(c.err, sizeof c.err, "chunk too large for one K1 launch"); return M2V_EINVAL; }
     CKC(c.d_recon0.reserve(G * fsz420)); CKC(c.d_recon1.reserve(g.P ? G * fsz420 : 16));
-    CKC(c.d_coefs.reserve(nmbF * 384)); CKC(c.d_mbinfo.reserve(nmbF)); CKC(c.d_mb_bits.reserve(nmbF)); CKC(c.d_mb_off.reserve(nmbF));
+    CKC(c.d_coefs.reserve(nmbF * 384)); CKC(c.d_mbinfo.reserve(nmbF)); CKC(c.d_mb_bits.reserve(nmbF)); CKC(c.d_mb_code.reserve((nmbF + 31) / 32 * 32 * M2V_MB_SLOT)); CKC(c.d_mb_off.reserve(nmbF));
     CKC(c.d_slice_off.reserve((size_t)F * g.mbh)); CKC(c.d_frame_bytes.reserve(F)); CKC(c.d_frame_off.reserve(F + 1));
     CKC(c.d_out[slot].reserve((nmbF * c.reserve_per_mb + 15) / 16 + 4));
     b.recon[0] = c.d_recon0.p; b.recon[1] = g.P ? c.d_recon1.p : c.d_recon0.p;
-    b.coefs = c.d_coefs.p; b.mbinfo = c.d_mbinfo.p; b.mb_bits = c.d_mb_bits.p; b.mb_off = c.d_mb_off.p;
+    b.coefs = c.d_coefs.p; b.mbinfo = c.d_mbinfo.p; b.mb_bits = c.d_mb_bits.p; b.mb_code = c.d_mb_code.p; b.mb_off = c.d_mb_off.p;
     b.slice_off = c.d_slice_off.p; b.frame_bytes = c.d_frame_bytes.p; b.frame_off = c.d_frame_off.p;
     b.out_words = (uint32_t *)c.d_out[slot].p; b.out_cap_words = c.d_out[slot].n * 4;
     b.k1_ctr = c.d_k1ctr.p; b.k1_grid_cap_i = c.grid_cap_i; b.k1_grid_cap_p = c.grid_cap_p;
@@ -174,6 +174,9 @@ int encode_enqueue(DevCtx &c, const Geom &g, const uint8_t *d_in, long F, long n
         CKC(cudaGetLastError());                                 // a failed K1 launch must not feed stale levels to the scans
     }
     if (c.timing) CKC(cudaEventRecord(c.ev_t[slot][1], c.st));
+    // (Measured and rejected: the count pass of frame t on a second stream beside K1 of frame t+1 - one K2 CTA fits next to the three
+    //  K1 CTAs of an SM.  The count pass leaves the critical path (0.355 -> 0.068 ms) but K1, bound by the pipes K2 also uses, slows down
+    //  by the same amount: 9.083 -> 9.067 ms per step.)
     { Range r("m2v K2 vlc count"); m2v_launch_k2(b, false, c.st); c.launches++; }
     if (c.timing) CKC(cudaEventRecord(c.ev_t[slot][2], c.st));
     {

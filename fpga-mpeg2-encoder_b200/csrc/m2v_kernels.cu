@@ -518,6 +518,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     //      vector = lane&7); round 1: chroma tiles on lanes 0..15 while lanes 16..31 run the same code on two
     //      all-zero dummy tiles (no predicate, no divergence, warp syncs with the constant full mask - a run-time
     //      mask makes the compiler guard every sync with MATCH/REDUX/VOTE).  (RTL:2029-2077, 2128-2356, 2452-2467)
+    // (Measured and rejected: THREE rounds of one pass each - rows of luma; rows of chroma beside columns of luma tiles 0,1; the other
+    //  columns - which saves one of four forward passes and the dummy tiles: the per-round overhead (roles, branches, syncs) outweighs
+    //  it, 1741 instead of 1665 instructions per macroblock, K1 +2.4 %.)
     // (Measured and rejected: unrolling the two rounds - the kernel no longer fits the instruction cache and slows down;
     //  predicating lanes 16..31 off in the chroma round, or syncing only the lower half-warp with __syncwarp(0xFFFF) held in a
     //  run-time mask - the compiler guards every such sync with MATCH/REDUX/VOTE.)
@@ -798,7 +801,7 @@ __device__ __forceinline__ void ac_code(int v, int run, uint32_t &code, int &len
 
 struct K2Args {
     const int16_t *coefs; const uint32_t *mbinfo;
-    uint32_t *mb_bits; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
+    uint32_t *mb_bits; uint32_t *mb_code; const uint32_t *mb_off; const uint32_t *slice_off; const unsigned long long *frame_off;
     uint32_t *out;
     int mbw, mbh, nmb, P; long n0; long total;
     long F; unsigned long long cap_words;                     // write pass: frames in the batch, capacity of `out` in 32-bit words
@@ -824,9 +827,20 @@ struct BitAcc {                       // MSB-first accumulator aligned to 32-bit
     }
     __device__ __forceinline__ void flush() { if (n) atomicOr(w, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123)); }
 };
-struct BitCount {
-    int n;
-    __device__ __forceinline__ void put(uint32_t, int len) { n += len; }
+// Count pass: besides the length it keeps the macroblock's own bitstring (MSB first, starting at bit 0) in a slot of M2V_MB_SLOT words,
+// interleaved over the 32 macroblocks of a warp so that lanes store and load the same word index side by side.  The write pass then only
+// shifts those words to the macroblock's place in the stream; a macroblock longer than the slot is walked a second time (BitAcc).
+struct BitLocal {
+    uint32_t *w; unsigned long long acc; int n, total, nw;
+    __device__ __forceinline__ void start(uint32_t *slot) { w = slot; acc = 0; n = 0; total = 0; nw = 0; }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        acc = (acc << len) | code; n += len; total += len;
+        if (n >= 32) {
+            if (nw < M2V_MB_SLOT) w[nw * 32] = (uint32_t)(acc >> (n - 32));
+            nw++; n -= 32; acc &= (1ull << n) - 1;
+        }
+    }
+    __device__ __forceinline__ void finish() { if (n && nw < M2V_MB_SLOT) w[nw * 32] = (uint32_t)(acc << (32 - n)); }
 };
 
 template <typename Emit>
@@ -921,22 +935,39 @@ __global__ void __launch_bounds__(128) k2_vlc(K2Args p) {
     const uint32_t info = __ldg(&p.mbinfo[gw]);
     const uint32_t li = bx > 0 ? __ldg(&p.mbinfo[gw - 1]) : 0u;
     const int16_t *zz = p.coefs + (size_t)gw * 384;
+    uint32_t *slot = p.mb_code + ((size_t)(gw >> 5) * M2V_MB_SLOT) * 32 + (gw & 31);
     if (!WRITE) {
-        BitCount bc; bc.n = 0;
-        mb_syntax(bc, zz, k, info, li, bx > 0);
-        p.mb_bits[gw] = (uint32_t)bc.n;
+        BitLocal bl; bl.start(slot);
+        mb_syntax(bl, zz, k, info, li, bx > 0);
+        bl.finish();
+        p.mb_bits[gw] = (uint32_t)bl.total;
     } else {
         const int hdr = (k == 0) ? 25 : 18;
         const unsigned long long pos = 8ull * (__ldg(&p.frame_off[f]) + hdr + __ldg(&p.slice_off[f * p.mbh + by])) + __ldg(&p.mb_off[gw]);
-        BitAcc bw; bw.start(p.out, pos);
-        mb_syntax(bw, zz, k, info, li, bx > 0);
-        bw.flush();
+        const int nw = (int)((p.mb_bits[gw] + 31) >> 5);
+        if (nw <= M2V_MB_SLOT) {                                  // the usual case: shift the cached words into place
+            uint32_t *W = p.out + (pos >> 5);
+            const int o = (int)(pos & 31);
+            uint32_t prev = 0;
+            for (int i = 0; i < nw; i++) {
+                const uint32_t L = slot[i * 32];
+                const uint32_t v = __funnelshift_r(L, prev, o);      // (prev << (32-o)) | (L >> o)
+                if (v) atomicOr(W + i, __byte_perm(v, 0, 0x0123));
+                prev = L;
+            }
+            const uint32_t v = __funnelshift_r(0u, prev, o);
+            if (v) atomicOr(W + nw, __byte_perm(v, 0, 0x0123));
+        } else {
+            BitAcc bw; bw.start(p.out, pos);
+            mb_syntax(bw, zz, k, info, li, bx > 0);
+            bw.flush();
+        }
     }
 }
 
 void m2v_launch_k2(const M2VBatch &b, bool write, cudaStream_t st) {
     K2Args a;
-    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
+    a.coefs = b.coefs; a.mbinfo = b.mbinfo; a.mb_bits = b.mb_bits; a.mb_code = b.mb_code; a.mb_off = b.mb_off; a.slice_off = b.slice_off;
     a.frame_off = b.frame_off; a.out = b.out_words;
     a.mbw = b.g.mbw; a.mbh = b.g.mbh; a.nmb = b.g.nmb; a.P = b.g.P; a.n0 = b.n0; a.total = b.F * b.g.nmb;
     a.F = b.F; a.cap_words = b.out_cap_words;

@@ -27,6 +27,7 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
     int16_t *coefs;            // [F][nmb][6][64] quantised levels, zig-zag order
     uint32_t *mbinfo;          // [F][nmb]
     uint32_t *mb_bits;         // [F][nmb]  bit length of each macroblock's syntax
+    uint32_t *mb_code;         // [ceil(F*nmb/32)][M2V_MB_SLOT][32]  the macroblocks' own bitstrings, cached by the count pass for the write pass
     uint32_t *mb_off;          // [F][nmb]  bit offset inside its slice (slice header included)
     uint32_t *slice_off;       // [F][mbh]  byte offset of slice inside the frame's slice area
     uint32_t *frame_bytes;     // [F]       slice-area bytes of the frame
@@ -38,6 +39,7 @@ struct M2VBatch {              // one call of encode_gops: frames [n0, n0+F)
                                // zeroes the other one for the launch after it (both zero before the first launch)
 };
 #define M2V_BODY_WORDS(total_bytes) ((total_bytes) / 4 + 4)   // words the body needs: its bytes, rounded up, plus slack for the last RED.OR
+#define M2V_MB_SLOT 32                // words of a macroblock's bitstring the count pass caches (1024 bits; longer ones are walked twice)
 #define M2V_K1_MAX_MBS (1l << 25)   // macroblocks per K1 launch: bound of the division-free index decode
 
 bool m2v_make_tmaps(M2VBatch &b);
