@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         uint32_t h0 = avg4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
         uint32_t h1 = avg4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
         uint32_t g0 = __shfl_xor_sync(FULL, h0, 1), g1 = __shfl_xor_sync(FULL, h1, 1);
-        if (!(r & 1)) { s.curC[comp][r >> 1][0] = avg4(g0, h0); s.curC[comp][r >> 1][1] = avg4(g1, h1); }
+        // mean2 is symmetric: the two lanes of a row pair hold the same result and both store it (same address, same value) - no branch
+        *(uint2 *)s.curC[comp][r >> 1] = make_uint2(avg4(g0, h0), avg4(g1, h1));
     }
     __syncwarp();
 
@@ -664,7 +665,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
 #pragma unroll
         for (int k = 0; k < 3; k++)
             if ((cbp << (2 * k + (lane >> 4))) & 32) dst[lane + 32 * k] = *(const uint2 *)&s.res[2 * k + (lane >> 4)][(lane & 15) * 4];
-        if (lane == 0) p.mbinfo[mbi] = M2V_INFO(inter, mvx, mvy, cbp);
+        const uint32_t info = M2V_INFO(inter, mvx, mvy, cbp);     // warp-uniform: packed in the uniform datapath, stored by one lane
+        if (elect_one()) p.mbinfo[mbi] = info;
     }
     __syncwarp();
     if (!more) break;
