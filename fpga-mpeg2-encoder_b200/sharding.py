@@ -42,7 +42,9 @@ def chunk_schedule(frames_per_rank, pframes_count, world, chunks, tail_gops=0):
     tail_gops > 0 (and chunks > 1) that last chunk is made small (tail_gops GOPs) and the others share the rest.
     Returns per rank the list of (first local frame, frames, absolute index of the first frame)."""
     gop = pframes_count + 1
-    gops = frames_per_rank // gop
+    gops = (frames_per_rank + gop - 1) // gop
+    tail_frames = gops * gop - frames_per_rank                   # a trailing partial GOP (end of the sequence): single rank only
+    assert tail_frames == 0 or world == 1, 'only the last rank of a sequence can hold a partial GOP'
     chunks = max(1, min(chunks, gops))
     if tail_gops > 0 and chunks > 1 and gops > tail_gops + (chunks - 2):
         base, extra = divmod(gops - tail_gops, chunks - 1)
@@ -50,6 +52,7 @@ def chunk_schedule(frames_per_rank, pframes_count, world, chunks, tail_gops=0):
     else:
         base, extra = divmod(gops, chunks)
         per = [(base + (1 if c < extra else 0)) * gop for c in range(chunks)]
+    per[-1] -= tail_frames
     out = [[] for _ in range(world)]
     n_abs = 0
     for c in range(chunks):

@@ -232,6 +232,11 @@ def test_chunk_schedule_covers_the_sequence_in_order(pkg):
         assert nabs == world * (F // gop) * gop
         if tail and len(sched[0]) > 1 and F // gop > tail + len(sched[0]) - 2:
             assert sched[0][-1][1] == tail * gop
+    # a trailing partial GOP (the end of a sequence, one rank): kept, in the last chunk
+    for (F, P, chunks) in ((120, 15, 2), (8, 15, 3), (1000, 15, 2), (17, 3, 4)):
+        sched = sharding.chunk_schedule(F, P, 1, chunks)[0]
+        assert sum(k for _, k, _ in sched) == F and all(k > 0 for _, k, _ in sched)
+        assert all(k % (P + 1) == 0 for _, k, _ in sched[:-1]) and [f for f, _, _ in sched] == [a for _, _, a in sched]
 
 
 _ARENA_WORKER = r'''
