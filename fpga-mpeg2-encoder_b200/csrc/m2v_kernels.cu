@@ -27,6 +27,10 @@ __constant__ uint32_t c_vlc_cbp[64];
 __constant__ uint32_t c_vlc_dcy[12];
 __constant__ uint32_t c_vlc_dcc[12];
 __device__ uint32_t d_vlc_ac[32 * M2V_AC_LEVELS];
+// (Measured and rejected: the entry packed into 8 bytes (recip; W | off << 8 | zz << 24) - the I-frame kernel is bound by shared-memory
+//  wavefronts and a 64-bit load takes half the wavefronts of a 128-bit one.  One I-frame launch under ncu 351 -> 339 us, but 1088 ->
+//  1146 instructions per macroblock for the unpacking, and config 2 (I-only) in the bench 175.7 -> 173.7 Gpixel/s:
+//  profiles/r02/k1_i_qentry8_experiment.txt.)
 struct QEntry { uint32_t W, recip, off, zz; };          // per coefficient position i*8+j
 __device__ QEntry d_qtab[4][64];                        // [Q_LEVEL-1]
 
