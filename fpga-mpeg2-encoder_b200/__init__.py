@@ -139,10 +139,10 @@ class Mpeg2Encoder:
     """One instance of the reference module: parameters are fixed at construction (RTL:11-14).  ndev > 1 spreads the
     instance over devices 0..ndev-1 of this process (m2v_create_multi); the stream is the same."""
 
-    def __init__(self, XL=6, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2, ndev=1):
+    def __init__(self, XL=6, YL=6, VECTOR_LEVEL=3, Q_LEVEL=2, ndev=1, force_multi=False):
         self._h = C.c_void_p()
         self.XL, self.YL, self.VECTOR_LEVEL, self.Q_LEVEL = XL, YL, VECTOR_LEVEL, Q_LEVEL
-        if ndev == 1:
+        if ndev == 1 and not force_multi:
             rc = lib().m2v_create(XL, YL, VECTOR_LEVEL, Q_LEVEL, C.byref(self._h))
         else:
             rc = lib().m2v_create_multi(ndev, XL, YL, VECTOR_LEVEL, Q_LEVEL, C.byref(self._h))

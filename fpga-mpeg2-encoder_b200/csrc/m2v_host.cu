@@ -476,13 +476,25 @@ extern "C" int m2v_kernel_ms(const m2v_encoder *e, float ms[5]) {
     memcpy(ms, e->w[0]->c.kms, sizeof e->w[0]->c.kms);
     return M2V_OK;
 }
+// A refused request is reported through the return value and must not linger as the runtime's "last error": the launch checks of
+// the encoder read that state.
 extern "C" void *m2v_alloc_host(size_t bytes) {
     void *p = nullptr;
-    return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+    cudaGetLastError();
+    return nullptr;
 }
-extern "C" void m2v_free_host(void *p) { if (p) cudaFreeHost(p); }
-extern "C" int m2v_register_host(void *p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? M2V_OK : M2V_ECUDA; }
-extern "C" int m2v_unregister_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? M2V_OK : M2V_ECUDA; }
+extern "C" void m2v_free_host(void *p) { if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError(); }
+extern "C" int m2v_register_host(void *p, size_t bytes) {
+    if (p && bytes && cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess) return M2V_OK;
+    cudaGetLastError();
+    return p && bytes ? M2V_ECUDA : M2V_EINVAL;
+}
+extern "C" int m2v_unregister_host(void *p) {
+    if (p && cudaHostUnregister(p) == cudaSuccess) return M2V_OK;
+    cudaGetLastError();
+    return p ? M2V_ECUDA : M2V_EINVAL;
+}
 
 // ---- framing helpers ---------------------------------------------------------------------------
 namespace {

@@ -285,13 +285,20 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     };
     for (int i = lane; i < 2 * RSTR / 2; i += 32) reinterpret_cast<uint32_t *>(&s.res[6][0])[i] = 0;    // dummy tiles: zero residual,
     for (int i = lane; i < 2 * PSTR / 4; i += 32) reinterpret_cast<uint32_t *>(&s.pred[6][0])[i] = 0;   // zero prediction
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
     // lane 0 draws the next index; the value is only looked at one macroblock later
     auto draw = [&]() { unsigned v = 0; if (lane == 0) v = nwarps + atomicAdd(p.ctr, 1u); return v; };
     MbPos cur = decode(gwarp);
     if (lane == 0) {
         mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Everything above is private to this launch (shared memory, arguments, a constant table).  From here on it reads what the launch
+    // before it wrote (the reconstruction, the work counter it zeroed for us) and writes what that launch may still be using (the other
+    // counter): wait for it to complete.  The next launch may start setting itself up behind this one at once.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
+    if (lane == 0) {
         fence_proxy_async();
         issue(cur, 0);
     }
@@ -752,7 +759,14 @@ static void launch_k1_t(const K1Args &a, const M2VBatch &b, int refk, cudaStream
     unsigned grid = (a.total + K1_WARPS - 1) / K1_WARPS;
     const unsigned cap = (unsigned)(PF ? b.k1_grid_cap_p : b.k1_grid_cap_i);
     if (grid > cap) grid = cap;
-    k1_mb_encode<VL, PF><<<grid, K1_WARPS * 32, k1_smem<VL, PF>(), st>>>(a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
+    // Programmatic dependent launch: the grid may be set up (CTAs resident, quantiser table and mbarriers in shared memory) behind the
+    // tail of the launch before it; it touches global memory only after griddepcontrol.wait, i.e. after that launch has completed.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(K1_WARPS * 32); cfg.dynamicSmemBytes = k1_smem<VL, PF>(); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k1_mb_encode<VL, PF>, a, b.tm_in, b.tm_refY[refk], b.tm_refC[refk]);
 }
 
 void m2v_launch_k1(const M2VBatch &b, int t, long ngops_t, unsigned seq, cudaStream_t st) {

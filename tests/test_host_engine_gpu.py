@@ -91,6 +91,55 @@ def test_pinned_source_and_pageable_source_agree(pkg, synth):
     pin.close(); enc.close()
 
 
+def test_multi_entry_point_with_one_device(pkg, ob, synth):
+    """m2v_create_multi(1, ...) is the same instance as m2v_create(...): same engine, same stream; out-of-range device counts are
+    refused (more devices than the box has: M2V_ENODEV, not a crash)"""
+    import torch
+    fr = synth.s4_edges(33, 11, 128, 80)
+    want = ob.encode(fr, 8, 5, 4, XL=6, YL=6)
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6, ndev=1, force_multi=True)
+    assert enc.device_count == 1
+    assert enc.encode_sequence(fr, 4) == want
+    enc.close()
+    n = torch.cuda.device_count()
+    for bad, code in [(0, pkg.M2V_EINVAL), (9, pkg.M2V_EINVAL)] + ([(n + 1, pkg.M2V_ENODEV)] if n < 8 else []):
+        with pytest.raises(pkg.M2VError) as ei:
+            pkg.Mpeg2Encoder(XL=6, YL=6, ndev=bad, force_multi=True)
+        assert ei.value.code == code, bad
+
+
+def test_macroblocks_longer_than_the_cached_slot(pkg, ob, synth):
+    """K2's count pass caches 1024 bits of a macroblock's bitstring for the write pass; white noise at Q_LEVEL=1 codes well
+    over 2000 bits per macroblock, so every macroblock takes the second walk - beside short ones in the same warp (a dark,
+    flat clip appended: a few dozen bits per macroblock)"""
+    W, H, P = 128, 96, 2
+    fr = np.concatenate([synth.s2_white(7, 4, W, H), synth.s3_dark(8, 5, W, H), synth.s2_white(9, 3, W, H)])
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6, VECTOR_LEVEL=1, Q_LEVEL=1)
+    got = enc.encode_sequence(fr, P)
+    enc.close()
+    assert got == ob.encode(fr, W // 16, H // 16, P, XL=6, YL=6, VL=1, Q=1)
+    assert len(got) * 8 / (len(fr) * (W // 16) * (H // 16)) > 1024
+
+
+def test_registered_host_memory_as_source_and_sink(pkg, ob, synth):
+    """m2v_register_host pins memory the caller owns (here numpy arrays): frames pushed from it, words drained into it"""
+    fr = np.ascontiguousarray(synth.s1_pan(12, 9, 160, 96))
+    sink = np.zeros(4 << 20, np.uint8)
+    L = pkg.lib()
+    assert L.m2v_register_host(fr.ctypes.data, fr.nbytes) == 0 and L.m2v_register_host(sink.ctypes.data, sink.nbytes) == 0
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    enc.begin(10, 6, 3)
+    enc.push_frames(fr); enc.sequence_stop()
+    n, last = enc.drain_into(sink)
+    assert last and sink[:n].tobytes() == ob.encode(fr, 10, 6, 3, XL=6, YL=6)
+    enc.close()
+    assert L.m2v_unregister_host(fr.ctypes.data) == 0 and L.m2v_unregister_host(sink.ctypes.data) == 0
+    assert L.m2v_register_host(0, 4096) != 0                       # refused, reported - and the handle after it works
+    enc = pkg.Mpeg2Encoder(XL=6, YL=6)
+    assert enc.encode_sequence(fr[:3], 1) == ob.encode(fr[:3], 10, 6, 1, XL=6, YL=6)
+    enc.close()
+
+
 def test_two_handles_on_two_devices_in_one_process(pkg, ob, synth):
     """the K1 launch configuration (dynamic shared memory attribute, persistent grid size) is per device: a second handle on
     another GPU of the same process must run P-frames too"""
