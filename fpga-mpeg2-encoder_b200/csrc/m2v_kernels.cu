@@ -288,17 +288,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     // lane 0 draws the next index; the value is only looked at one macroblock later
     auto draw = [&]() { unsigned v = 0; if (lane == 0) v = nwarps + atomicAdd(p.ctr, 1u); return v; };
     MbPos cur = decode(gwarp);
-    if (lane == 0) {
-        mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     // Everything above is private to this launch (shared memory, arguments, a constant table).  From here on it reads what the launch
     // before it wrote (the reconstruction, the work counter it zeroed for us) and writes what that launch may still be using (the other
     // counter): wait for it to complete.  The next launch may start setting itself up behind this one at once.
+    // (The mbarriers are initialised after the wait as well: with them before it compute-sanitizer's racecheck reports hazards between
+    // mbarrier.init and the first expect_tx of the same lane - two grids resident at once - and the two instructions are not worth it.)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.ctr_next = 0;                  // nobody touches the other counter during this launch
     if (lane == 0) {
+        mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
         issue(cur, 0);
     }
