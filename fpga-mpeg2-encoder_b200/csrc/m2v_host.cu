@@ -783,7 +783,15 @@ extern "C" int m2v_push_frames(m2v_encoder *e, const uint8_t *yuv, long nframes)
         // several devices: cut the push into at least one batch per device
         long bf = e->batch_frames;
         if (e->ndev > 1) bf = std::max(gopf, std::min(bf, (direct / gopf + e->ndev - 1) / e->ndev * gopf));
-        for (long f0 = 0; f0 < direct; f0 += bf) deal(e, yuv + (size_t)f0 * fsz, std::min(bf, direct - f0), -1);
+        // the kernels of the LAST batch of a push overlap nothing (the caller comes back for more, or stops): it is cut in two
+        // halves so that what is left exposed is half as long
+        bool halved = false;
+        for (long f0 = 0; f0 < direct;) {
+            long n = std::min(bf, direct - f0);
+            if (!halved && n == direct - f0 && n >= 2 * gopf) { n = (n / gopf + 1) / 2 * gopf; halved = true; }
+            deal(e, yuv + (size_t)f0 * fsz, n, -1);
+            f0 += n;
+        }
         {
             Range r("m2v push_frames: wait for the copies");
             std::unique_lock<std::mutex> lk(e->mu);
@@ -837,11 +845,11 @@ namespace {
 // segments -> caller's buffer.  A long stretch (tens of MB after a big push) is copied by a few threads: one core moves
 // ~10 GB/s, and this copy sits on the critical path of the end-to-end time after the last kernel.
 void copy_out(uint8_t *dst, const uint8_t *src, size_t n) {
-    const size_t kMin = (size_t)2 << 20;
+    const size_t kMin = (size_t)1 << 20;
     if (n < 2 * kMin) { memcpy(dst, src, n); return; }
-    const int parts = (int)std::min<size_t>(4, n / kMin);
+    const int parts = (int)std::min<size_t>(8, n / kMin);
     const size_t per = (n / parts + 63) & ~(size_t)63;
-    std::thread th[3];
+    std::thread th[7];
     for (int i = 1; i < parts; i++) {
         const size_t o = (size_t)i * per, len = std::min(per, n - o);
         th[i - 1] = std::thread([=] { memcpy(dst + o, src + o, len); });
