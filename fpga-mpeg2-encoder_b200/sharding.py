@@ -107,11 +107,21 @@ class HostArena:
     know where my body goes"."""
     TABLE = 1 << 16
 
-    def __init__(self, pkg, name, nbytes, rank, world, rows=64, pin=True):
+    def __init__(self, pkg, name, nbytes, rank, world, rows=64, pin=True, directory='/dev/shm'):
         self.pkg, self.rank, self.world, self.rows, self.pinned = pkg, rank, world, rows, pin
-        self.path = '/dev/shm/' + name
         self.nbytes = self.TABLE + nbytes
         assert rows * world * 16 + world * 16 <= self.TABLE
+        self.mm = self._pin = None
+        if directory is None:                                     # one process: private pinned memory, nothing to share
+            assert world == 1
+            self._pin = pkg.PinnedArray(self.nbytes)
+            self.buf = self._pin.array
+            self.buf[:self.TABLE] = 0
+            self.addr = self._pin.ptr
+            self.pinned = False
+            self._views()
+            return
+        self.path = os.path.join(directory, name)
         if rank == 0:                                             # callers put a barrier between rank 0's constructor and the others'
             fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
             os.ftruncate(fd, self.nbytes)
@@ -126,6 +136,10 @@ class HostArena:
             rc = pkg.lib().m2v_register_host(self.addr, self.nbytes)
             if rc:
                 raise pkg.M2VError(rc, 'm2v_register_host(host arena)')
+        self._views()
+
+    def _views(self):
+        rows, world = self.rows, self.world
         self.table = self.buf[:rows * world * 16].view(np.int64).reshape(rows, world, 2)
         self.flags = self.buf[rows * world * 16:rows * world * 16 + world * 16].view(np.int64).reshape(world, 2)
         self.stream = self.buf[self.TABLE:]
@@ -155,6 +169,10 @@ class HostArena:
                 raise TimeoutError('host arena: barrier %d' % epoch)
 
     def close(self):
+        if getattr(self, '_pin', None) is not None:
+            self.table = self.flags = self.stream = self.buf = None
+            self._pin.close(); self._pin = None
+            return
         if getattr(self, 'mm', None) is None:
             return
         if self.pinned:
