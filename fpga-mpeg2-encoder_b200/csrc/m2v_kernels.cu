@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
         issue(cur, 0);
     }
     unsigned nidx = __shfl_sync(FULL, draw(), 0);                              // index of the macroblock after this one
-    uint32_t phase = 0;
+    uint32_t it = 0;                                                           // macroblocks done by this warp: stage it & 1, mbarrier parity (it >> 1) & 1
     int stg = 0;
 #pragma unroll 1
     for (;; stg ^= 1) {
@@ -321,14 +321,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PFRAME ? 3 : 4) k1_mb_encode(K1
     StageSmem &S = s.st[stg];
     int32_t *tmp;
     if constexpr (PFRAME) tmp = reinterpret_cast<int32_t *>(&S.winC[0][0][0]); else tmp = reinterpret_cast<int32_t *>(s.scratch);
-    mbar_wait(smem_u32(&bars[stg]), (phase >> stg) & 1u);
-    phase ^= 1u << stg;
+    mbar_wait(smem_u32(&bars[stg]), (it >> 1) & 1u);
+    it++;
 
     // ---- current block: Y as is; U,V 4:4:4 -> 4:2:0 = mean2 of pixel pairs, then mean2 of the two
     //      horizontally subsampled rows (RTL:1086-1089, 1167-1170) -------------------------------
     {
         const int comp = lane >> 4, r = lane & 15;
-        uint4 v = *(const uint4 *)(comp ? S.curV[r] : S.curU[r]);
+        uint4 v = reinterpret_cast<const uint4 *>(S.curU)[lane];      // curV follows curU: row r of plane comp = 16-byte row `lane`
         uint32_t h0 = avg4(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.x, v.y, 0x7531));
         uint32_t h1 = avg4(__byte_perm(v.z, v.w, 0x6420), __byte_perm(v.z, v.w, 0x7531));
         uint32_t g0 = __shfl_xor_sync(FULL, h0, 1), g1 = __shfl_xor_sync(FULL, h1, 1);
