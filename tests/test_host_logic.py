@@ -148,6 +148,47 @@ def test_biased_residual_transform_identity():
     assert (Mx @ rows == Mx @ (R @ Mx.T)).all()
 
 
+def test_cached_bitstring_shift_copy_identity():
+    """K2: the count pass keeps each macroblock's bitstring MSB-first in 32-bit words (last word left-aligned, zero padded); the write
+    pass ORs word j = funnelshift_r(L_j, L_(j-1), o) into stream word W0+j, o = bit position & 31, plus one trailing word, byte-swapped
+    into wire order.  Replayed in Python on random code sequences: the ORed words equal the plain concatenation of all bits."""
+    rng = np.random.default_rng(13)
+    def funnelshift_r(lo, hi, s):
+        return (((hi << 32) | lo) >> (s & 31)) & 0xFFFFFFFF
+    for trial in range(300):
+        nmb = int(rng.integers(1, 12))
+        start = int(rng.integers(0, 97))                           # bit position of the first macroblock (after headers)
+        stream_bits, words, pos = [0] * start, {}, start
+        for _ in range(nmb):
+            codes = [(int(rng.integers(0, 1 << l)), int(l)) for l in rng.integers(1, 25, int(rng.integers(1, 40)))]
+            # count pass (BitLocal)
+            acc = n = 0; L = []
+            for c, l in codes:
+                acc = (acc << l) | c; n += l
+                if n >= 32:
+                    L.append((acc >> (n - 32)) & 0xFFFFFFFF); n -= 32; acc &= (1 << n) - 1
+            total = sum(l for _, l in codes)
+            if n:
+                L.append((acc << (32 - n)) & 0xFFFFFFFF)
+            assert len(L) == (total + 31) // 32
+            # write pass
+            W0, o, prev = pos >> 5, pos & 31, 0
+            for j, Lj in enumerate(L):
+                v = funnelshift_r(Lj, prev, o)
+                words[W0 + j] = words.get(W0 + j, 0) | v
+                prev = Lj
+            v = funnelshift_r(0, prev, o)
+            words[W0 + len(L)] = words.get(W0 + len(L), 0) | v
+            for c, l in codes:
+                stream_bits += [(c >> (l - 1 - i)) & 1 for i in range(l)]
+            pos += total
+        want = stream_bits + [0] * (-len(stream_bits) % 32)
+        for w in range(len(want) // 32):
+            expect = int(''.join(map(str, want[32 * w:32 * w + 32])), 2)
+            assert words.get(w, 0) == expect, (trial, w)
+        assert all(v == 0 for k, v in words.items() if k >= len(want) // 32)
+
+
 def test_index_decode_is_exact():
     """K1 turns a drawn macroblock index into (GOP, row, column) with umulhi(n, ceil(2^32/d)), d = macroblocks per row /
     rows per frame (4..128): exact for every n below 2^25 = M2V_K1_MAX_MBS, the per-launch bound the host enforces."""
